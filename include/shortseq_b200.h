@@ -1,0 +1,201 @@
+/*
+ * shortseq_b200.h -- C ABI of the B200-native ShortSeq hot path
+ * (batched pack / dedup-count / Hamming / decode of short reads).
+ *
+ * The reference (AlexTate/ShortSeq) has no FFI layer: its boundary is the
+ * CPython type protocol of its Cython classes.  Each entry point below names
+ * the reference function(s) whose per-object work it performs for a whole
+ * batch (paths relative to the reference repo, file:line).  INTEGRATION.md
+ * shows the Cython `cdef extern` / ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only.  Unless a name says `host`, every data
+ *    pointer is a DEVICE pointer on the context's GPU and the call only
+ *    ENQUEUES work on the context's stream; nothing is read back until
+ *    ssq_ctx_sync().  The caller owns every buffer; the library owns only
+ *    contexts and counters.
+ *  - Return value: SSQ_OK or an SSQ_ERR_* for errors detectable at enqueue
+ *    time (bad argument, CUDA launch failure).  DATA errors (non-ACGT base,
+ *    over-long read, length mismatch, table overflow) are recorded on the
+ *    device and reported by the next ssq_ctx_sync() for the LOWEST read index,
+ *    which is the read the reference's serial loop would have raised on
+ *    (counter.pyx:23-29).
+ *  - Batch input format: one contiguous uint8 ASCII buffer holding the reads
+ *    back to back plus int64 offsets[n+1]; read i is
+ *    ascii[offsets[i] .. offsets[i+1]).
+ *  - Packed layout (util.pyx:109-118,133-138): base j of a read lives in bits
+ *    [2(j%32), 2(j%32)+1] of 64-bit word j/32, code = (c>>1)&3 (A0 C1 T2 G3),
+ *    unused high bits zero.  ShortSeq64: 1 word/read (0..32 nt).  ShortSeq192:
+ *    3 words/read, AoS words[n][3], unused words zero (33..96 nt).
+ *    ShortSeqVar: CSR, words[word_off[i] .. word_off[i+1]) with
+ *    ceil(len/32) words (97..1024 nt).
+ *  - There is no CPU fallback: without a CUDA device every compute call fails
+ *    with SSQ_ERR_CUDA.
+ */
+#ifndef SHORTSEQ_B200_H
+#define SHORTSEQ_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSQ_ABI_VERSION 1
+
+/* status codes */
+#define SSQ_OK 0
+#define SSQ_ERR_BAD_BASE 1      /* "Unsupported base character" (short_seq_64.pyx:105, util.pyx:115,137) */
+#define SSQ_ERR_TOO_LONG 2      /* "Sequences longer than 1024 bases are not supported." (short_seq.pyx:74) */
+#define SSQ_ERR_CLASS 3         /* read length outside the container class of the call (or negative) */
+#define SSQ_ERR_CUDA 4          /* CUDA runtime error / no device; see ssq_last_error() */
+#define SSQ_ERR_LEN_MISMATCH 5  /* "Hamming distance requires sequences of equal length" (short_seq_64.pyx:78-80) */
+#define SSQ_ERR_TABLE_FULL 6    /* counter overflowed beyond recovery; the counter must be discarded */
+#define SSQ_ERR_ARG 7           /* invalid argument */
+
+/* container classes (short_seq.pyx:54-74) */
+#define SSQ_CLASS_64 0   /* 0..32 nt   */
+#define SSQ_CLASS_192 1  /* 33..96 nt  */
+#define SSQ_CLASS_VAR 2  /* 97..1024 nt */
+
+typedef struct ssq_ctx ssq_ctx;         /* one GPU + one stream + error state */
+typedef struct ssq_counter ssq_counter; /* device hash table of (len, words) -> count */
+
+/* Result of ssq_ctx_sync(): the first data error in read order since the last sync. */
+typedef struct ssq_report {
+    int32_t code;          /* SSQ_OK or the SSQ_ERR_* of the lowest failing read */
+    int32_t reserved;
+    int64_t first_bad_read; /* index of that read within its call's batch, or -1 */
+} ssq_report;
+
+/* ---- library / context ------------------------------------------------- */
+int ssq_abi_version(void);
+const char *ssq_last_error(void);      /* thread-local message for the last SSQ_ERR_CUDA / SSQ_ERR_ARG */
+int ssq_device_count(int *count);
+int ssq_ctx_create(int device, ssq_ctx **out);
+int ssq_ctx_destroy(ssq_ctx *ctx);
+/* Use an externally owned cudaStream_t (e.g. the caller framework's current stream); NULL restores the context's own. */
+int ssq_ctx_set_stream(ssq_ctx *ctx, void *cuda_stream);
+void *ssq_ctx_stream(ssq_ctx *ctx);
+/* Wait for all enqueued work, fetch and clear the device error record. */
+int ssq_ctx_sync(ssq_ctx *ctx, ssq_report *report);
+
+/* device / pinned-host memory helpers for callers that have no CUDA binding of their own */
+int ssq_malloc(ssq_ctx *ctx, size_t bytes, void **dptr);
+int ssq_free(ssq_ctx *ctx, void *dptr);
+int ssq_host_alloc(size_t bytes, void **hptr);   /* pinned */
+int ssq_host_free(void *hptr);
+int ssq_memcpy_h2d(ssq_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on ctx stream */
+int ssq_memcpy_d2h(ssq_ctx *ctx, void *dst, const void *src, size_t bytes); /* async on ctx stream */
+int ssq_memset(ssq_ctx *ctx, void *dst, int value, size_t bytes);
+
+/* ---- packing ------------------------------------------------------------
+ * Replaces, for a whole batch: short_seq.pyx:54-74 (_new) ->
+ * short_seq_64.pyx:96-108 (_marshall_bytes_64) / short_seq_192.pyx:103-108 ->
+ * util.pyx:78-140 (_marshall_bytes_array, _marshall_full_blocks,
+ * _marshall_partial_block), with validation (util.pxd:98-127) fused into the
+ * same pass.  Validation is EXACT {A,C,G,T}; the reference's bloom filter also
+ * lets 16 alias byte values through with undefined results (SURVEY trap T1).
+ * ascii_bytes = size of the ASCII buffer (so vector loads never leave it). */
+int ssq_pack64(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,
+               int64_t n, uint64_t *words /*[n]*/, uint8_t *lens /*[n]*/);
+int ssq_pack192(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,
+                int64_t n, uint64_t *words /*[n][3]*/, uint8_t *lens /*[n]*/);
+/* ShortSeqVar (short_seq_var.pyx:123-132).  word_off[n+1] is an OUTPUT (exclusive scan of
+ * ceil(len/32)); words must hold at least ssq_packvar_words_bound(ascii_bytes, n) entries. */
+int64_t ssq_packvar_words_bound(int64_t ascii_bytes, int64_t n);
+int ssq_packvar(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,
+                int64_t n, int64_t *word_off /*[n+1]*/, uint64_t *words, uint16_t *lens /*[n]*/);
+
+/* ---- decoding -------------------------------------------------------------
+ * Replaces short_seq_64.pyx:114-121, short_seq_192.pyx:114-127,
+ * short_seq_var.pyx:98-120 (charmap util.pyx:52).  out_offsets[n+1] is the
+ * exclusive scan of lens, produced by ssq_lens_to_offsets. */
+int ssq_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes /*1|2*/, int64_t n,
+                        int64_t *out_offsets /*[n+1]*/);
+int ssq_decode64(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n,
+                 const int64_t *out_offsets, uint8_t *ascii_out);
+int ssq_decode192(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n,
+                  const int64_t *out_offsets, uint8_t *ascii_out);
+int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, const uint16_t *lens,
+                  int64_t n, const int64_t *out_offsets, uint8_t *ascii_out);
+
+/* ---- Hamming distance (the `^` operator) ----------------------------------
+ * Replaces short_seq_64.pyx:77-84, short_seq_192.pyx:74-91, short_seq_var.pyx:64-81:
+ * sum over blocks of popcount(((x>>1)|x) & 0x5555...), x = a^b.  Pairs with different
+ * lengths record SSQ_ERR_LEN_MISMATCH (their dist is written as the all-ones value). */
+int ssq_hamming_pairs64(ssq_ctx *ctx, const uint64_t *a, const uint8_t *len_a, const uint64_t *b,
+                        const uint8_t *len_b, int64_t n, uint8_t *dist);
+int ssq_hamming_pairs192(ssq_ctx *ctx, const uint64_t *a, const uint8_t *len_a, const uint64_t *b,
+                         const uint8_t *len_b, int64_t n, uint8_t *dist);
+int ssq_hamming_pairsvar(ssq_ctx *ctx, const uint64_t *a, const int64_t *a_off, const uint16_t *len_a,
+                         const uint64_t *b, const int64_t *b_off, const uint16_t *len_b, int64_t n,
+                         uint16_t *dist);
+/* Each query against a reference set of nr sequences (UMI-collapse style).  Only refs of the
+ * query's length are comparable; min_dist = 255 / argmin = 0xFFFFFFFF when there is none.
+ * Ties keep the lowest ref index.  n_within (optional, may be NULL) = number of refs at
+ * distance <= thresh.  words_per_seq is 1 (ShortSeq64) or 3 (ShortSeq192). */
+int ssq_hamming_refset(ssq_ctx *ctx, int words_per_seq, const uint64_t *q, const uint8_t *len_q,
+                       int64_t nq, const uint64_t *refs, const uint8_t *len_r, int32_t nr,
+                       int32_t thresh, uint8_t *min_dist, uint32_t *argmin, uint32_t *n_within);
+
+/* ---- dedup counting --------------------------------------------------------
+ * Replaces ShortSeqCounter (counter.pyx:10-54): key = (length, words) -- the reference's
+ * __eq__ (short_seq_64.pyx:41-44, short_seq_192.pyx:35-41); value = multiplicity.  The
+ * reference's dict slot hash (word0, util.pxd:68-70) is not observable; the table mixes
+ * its own.  klass is SSQ_CLASS_64 or SSQ_CLASS_192 (the reference never deduplicates
+ * ShortSeqVar, SURVEY trap T3).  expected_unique sizes the table (it grows if exceeded);
+ * hash_rot (0..56) rotates the slot hash so that a table holding only the keys of one
+ * hash partition (multi-GPU owner tables) still spreads over all slots. */
+int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int hash_rot,
+                       ssq_counter **out);
+int ssq_counter_destroy(ssq_counter *c);
+int ssq_counter_clear(ssq_counter *c);
+/* count already packed reads (counter.pyx:31-33 _count_short_seq_vector) */
+int ssq_counter_insert(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n);
+/* add weighted keys: counts[i] occurrences of key i (merge step of the multi-GPU counter) */
+int ssq_counter_merge(ssq_counter *c, const uint64_t *words, const uint8_t *lens,
+                      const uint64_t *counts, int64_t n);
+/* fused pack + count (counter.pyx:23-29 _count_py_bytes_list): also emits the packed batch */
+int ssq_counter_pack_count(ssq_counter *c, const uint8_t *ascii, int64_t ascii_bytes,
+                           const int64_t *offsets, int64_t n, uint64_t *words, uint8_t *lens);
+/* record, per key, the lowest (base_index + i) at which it occurs in this packed batch, so
+ * that exports can be put in the reference's dict order (first occurrence). */
+int ssq_counter_first_index(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n,
+                            int64_t base_index);
+/* counts of the given keys (0 when absent): dict lookup / `in` */
+int ssq_counter_lookup(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n,
+                       uint64_t *counts);
+/* number of distinct keys; synchronises the context (data errors stay pending) */
+int ssq_counter_size(ssq_counter *c, int64_t *n_unique);
+int ssq_counter_capacity(ssq_counter *c, int64_t *slots);
+/* Export all (key, len, count[, first_idx]) tuples, grouped into n_parts hash partitions
+ * (owner = top log2(n_parts) bits of the key hash; n_parts a power of two, 1 = no
+ * grouping).  Buffers must hold ssq_counter_size() tuples; part_counts[n_parts] (device)
+ * receives the tuples per partition; first_idx may be NULL. */
+int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *lens,
+                       uint64_t *counts, int64_t *first_idx, int64_t *part_counts);
+
+/* ---- host-buffer pipeline ---------------------------------------------------
+ * The call a host-language binding makes with HOST memory: chunks the batch,
+ * overlaps host->device copies, the fused pack+count kernel and the
+ * device->host copy of the packed words/lens on separate streams, and
+ * returns after everything completed (report filled as by ssq_ctx_sync).
+ * h_words / h_lens may be NULL when only the counts are wanted.  Pinned host
+ * buffers (ssq_host_alloc) give full PCIe bandwidth. */
+int ssq_host_pack_count(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii,
+                        const int64_t *h_offsets, int64_t n, uint64_t *h_words, uint8_t *h_lens,
+                        int64_t chunk_reads, ssq_report *report);
+
+/* ---- synthetic reads (measurement tooling) ----------------
+ * Deterministic counter-based generator, identical to oracle/ssq_oracle.c's
+ * ssq_oracle_synth_reads.  offsets[n+1] and ascii are outputs; ascii must hold
+ * n*len_hi bytes. */
+int ssq_synth_reads(ssq_ctx *ctx, uint64_t seed, int64_t first_read, int64_t n, int64_t n_keys,
+                    int32_t len_lo, int32_t len_hi, int64_t *offsets, uint8_t *ascii);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHORTSEQ_B200_H */

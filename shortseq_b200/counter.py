@@ -1,0 +1,219 @@
+"""Dedup counting: the drop-in ShortSeqCounter and the device-resident DeviceCounter behind it.
+
+Reference: shortseq/counter.pyx:10-71.  The reference fills a Python dict serially
+(pack, dict probe, PyLong increment per read); here the whole list goes through the fused
+pack+count kernel and only the uniques are boxed into ShortSeq objects.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import batch as _batch
+from ._lib import CLASS_64, CLASS_192, CLASS_VAR
+from ._runtime import MSG_TOO_LONG, context, gather_reads, ptr, words_to_numpy
+from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box
+
+
+class DeviceCounter:
+    """A GPU hash table of (length, packed words) -> count for one container class.
+
+    klass: CLASS_64 or CLASS_192 (the reference never deduplicates ShortSeqVar keys,
+    SURVEY trap T3).  expected_unique sizes the table; it grows when exceeded.
+    """
+
+    def __init__(self, klass, expected_unique=0, hash_rot=0, device=None):
+        if klass not in (CLASS_64, CLASS_192):
+            raise ValueError("DeviceCounter supports CLASS_64 and CLASS_192")
+        self.ctx = context(device)
+        self.klass = klass
+        self.W = 1 if klass == CLASS_64 else 3
+        h = C.c_void_p()
+        _lib.check(_lib.lib().ssq_counter_create(self.ctx.bind(), klass, int(expected_unique), int(hash_rot), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().ssq_counter_destroy(h)
+            except Exception:  # noqa: BLE001 -- interpreter shutdown
+                pass
+            self.handle = None
+
+    # -- updates ------------------------------------------------------------------------------
+    def pack_count(self, source, offsets=None, check=True):
+        """Fused pack + count of a batch of reads of this counter's class -> ShortSeqArray."""
+        b = _batch.ReadBatch.make(source, offsets, self.ctx.device)
+        words, lens = _batch._alloc_out(self.ctx, self.klass, b.n)
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_pack_count(self.handle, ptr(b.ascii), int(b.ascii.numel()), ptr(b.offsets),
+                                                    b.n, ptr(words), ptr(lens)))
+        if check:
+            _batch.raise_for_report(self.ctx.sync(), b)
+        return _batch.ShortSeqArray(self.ctx, self.klass, words, lens)
+
+    def insert(self, arr, check=True):
+        """Count an already packed ShortSeqArray."""
+        if arr.klass != self.klass:
+            raise TypeError("array class does not match the counter class")
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_insert(self.handle, ptr(arr.words), ptr(arr.lens), len(arr)))
+        if check:
+            _batch.raise_for_report(self.ctx.sync())
+
+    def merge(self, words, lens, counts):
+        """Add weighted keys (tensors on this device): counts[i] occurrences of key i."""
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_merge(self.handle, ptr(words), ptr(lens), ptr(counts), int(lens.numel())))
+        _batch.raise_for_report(self.ctx.sync())
+
+    def track_first_index(self, arr, base_index=0):
+        """Record the first occurrence index of every key over this packed batch (dict order)."""
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_first_index(self.handle, ptr(arr.words), ptr(arr.lens), len(arr), int(base_index)))
+
+    # -- queries ------------------------------------------------------------------------------
+    def __len__(self):
+        n = C.c_int64()
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_size(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def capacity(self):
+        n = C.c_int64()
+        _lib.check(_lib.lib().ssq_counter_capacity(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def lookup(self, arr):
+        """Counts of the keys in arr (0 when absent) -> int64 tensor."""
+        out = self.ctx.empty((len(arr),), torch.int64)
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_lookup(self.handle, ptr(arr.words), ptr(arr.lens), len(arr), ptr(out)))
+        _batch.raise_for_report(self.ctx.sync())
+        return out
+
+    def export(self, n_parts=1, with_first_index=False):
+        """All (key, len, count) tuples grouped by hash partition.
+
+        -> (ShortSeqArray keys, counts int64 tensor, first_idx int64 tensor or None, part_counts int64 tensor).
+        Partition p (the owner of a key in a p-way multi-GPU merge) is the slice
+        [sum(part_counts[:p]), sum(part_counts[:p+1])).
+        """
+        n = len(self)
+        ctx = self.ctx
+        words = ctx.empty((n,) if self.klass == CLASS_64 else (n, 3), torch.int64)
+        lens = ctx.empty((n,), torch.uint8)
+        counts = ctx.empty((n,), torch.int64)
+        first = ctx.empty((n,), torch.int64) if with_first_index else None
+        parts = ctx.empty((n_parts,), torch.int64)
+        ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_export(self.handle, int(n_parts), ptr(words), ptr(lens), ptr(counts), ptr(first),
+                                                ptr(parts)))
+        _batch.raise_for_report(ctx.sync())
+        return _batch.ShortSeqArray(ctx, self.klass, words, lens), counts, first, parts
+
+
+def count_reads(reads, device=None):
+    """Count a list of bytes of mixed lengths on the GPU.
+
+    -> list of (klass, words tuple, length, count, first_index) in first-occurrence order.
+    ShortSeqVar-length reads cannot be deduplicated by the reference (its dict hashes the heap
+    pointer, SURVEY trap T3); they are rejected here rather than silently diverging.
+    """
+    h_ascii, h_off = gather_reads(reads)
+    lens = np.diff(h_off)
+    errors = []
+    too_long = np.nonzero(lens > 1024)[0]
+    if too_long.size:
+        errors.append((int(too_long[0]), Exception(MSG_TOO_LONG)))
+    var = np.nonzero((lens > 96) & (lens <= 1024))[0]
+    if var.size:
+        errors.append((int(var[0]), NotImplementedError(
+            "ShortSeqCounter: reads longer than 96 nt (ShortSeqVar) are not counted -- the reference does not "
+            "deduplicate them either (each occurrence becomes its own key)")))
+    out = []
+    for k, idx, sub_ascii, sub_off in _batch.split_by_class(h_ascii, h_off):
+        if k == CLASS_VAR:
+            continue
+        ctr = DeviceCounter(k, expected_unique=min(idx.size, 1 << 26), device=device)
+        b = _batch.ReadBatch.make(sub_ascii, sub_off, ctr.ctx.device)
+        arr = ctr.pack_count(b, check=False)
+        rep = ctr.ctx.sync()
+        if rep.code != _lib.OK:
+            try:
+                _batch.raise_for_report(rep, b, idx)
+            except Exception as e:  # noqa: BLE001 -- re-raised below in list order
+                errors.append((int(idx[int(rep.first_bad_read)]), e))
+            continue
+        ctr.track_first_index(arr)
+        keys, counts, first, _ = ctr.export(1, with_first_index=True)
+        w, l, _ = keys.to_host()
+        cnt = counts.cpu().numpy()
+        fi = idx[first.cpu().numpy()]          # position in the original list
+        for j in range(len(l)):
+            words = (int(w[j]),) if k == CLASS_64 else tuple(int(x) for x in w[j])
+            out.append((k, words, int(l[j]), int(cnt[j]), int(fi[j])))
+    if errors:
+        raise min(errors, key=lambda t: t[0])[1]
+    out.sort(key=lambda t: t[4])
+    return out
+
+
+class ShortSeqCounter(dict):
+    """dict of ShortSeq -> count, filled from a list of bytes (reference counter.pyx:10-54).
+
+    Like the reference, only `type(source) is list` is consumed, elements must be bytes, and
+    the first bad read (in list order) aborts construction with the reference's exception.
+    Items iterate in first-occurrence order.
+    """
+
+    def __init__(self, source=None):
+        super().__init__()
+        if type(source) is list:
+            self._count_py_bytes_list(source)
+
+    def __setitem__(self, key, val):
+        if type(key) not in (ShortSeq64, ShortSeq192, ShortSeqVar):
+            raise TypeError(f"{self.__class__} does not support {type(key)} keys")
+        dict.__setitem__(self, key, val)
+
+    def _count_py_bytes_list(self, it):
+        if not it:
+            return
+        for klass, words, length, count, _ in count_reads(it):
+            key = _box(klass, words, length)
+            dict.__setitem__(self, key, dict.get(self, key, 0) + count)
+
+    @classmethod
+    def from_batch(cls, source, offsets=None, klass=None, device=None):
+        """Count a class-homogeneous batch given as ASCII buffer + offsets (no list of bytes needed)."""
+        b = _batch.ReadBatch.make(source, offsets, device)
+        if klass is None:
+            klass = CLASS_64 if b.n == 0 else _batch.class_of_length(int(b.lengths_host()[0]))
+        ctr = DeviceCounter(klass, expected_unique=min(b.n, 1 << 26), device=b.ctx.device)
+        arr = ctr.pack_count(b)
+        ctr.track_first_index(arr)
+        keys, counts, first, _ = ctr.export(1, with_first_index=True)
+        w, l, _ = keys.to_host()
+        cnt, fi = counts.cpu().numpy(), first.cpu().numpy()
+        self = cls()
+        for j in np.argsort(fi, kind="stable"):
+            words = (int(w[j]),) if klass == CLASS_64 else tuple(int(x) for x in w[j])
+            dict.__setitem__(self, _box(klass, words, int(l[j])), int(cnt[j]))
+        return self
+
+
+def read_and_count_fastq(filename):
+    """Count the sequence lines of a FASTQ file (reference counter.pyx:57-71, fast_read.pyx:3-20).
+
+    Every 4k+2-th line is a read; like the reference's `_from_chars`, the last byte of the line
+    (the newline) is dropped unconditionally (SURVEY trap T9).
+    """
+    reads = []
+    with open(filename, "rb") as f:
+        for count, line in enumerate(f, start=1):
+            if count % 2 == 0 and count % 4 != 0:
+                reads.append(line[:-1])
+    return ShortSeqCounter(reads)

@@ -1,0 +1,399 @@
+// ssq_codec.cu -- batched decode (2-bit -> ASCII), Hamming distance, synthetic reads.
+#include "ssq_internal.h"
+
+namespace ssq {
+
+constexpr int kThreads = 256;
+
+// =============================================================================================
+// Decode.  Replaces the reference's per-object __str__ (short_seq_64.pyx:114-121,
+// short_seq_192.pyx:114-127, short_seq_var.pyx:98-120; charmap "ACTG", util.pyx:52).
+//
+// Mirror image of the pack kernel: the tile's output bytes form one contiguous range.
+//   A. every read ORs its 2*len code bits into a shared-memory bit stream at the bit position
+//      of its first output byte (reads abut at arbitrary 2-bit positions, hence atomicOr);
+//   B. the stream is expanded 32 bits -> 16 ASCII bytes per thread with byte-permute lookups
+//      and written with aligned 16-byte stores (edge chunks byte-wise: they are shared with
+//      the neighbouring tiles).
+// =============================================================================================
+
+// 8 bits of codes (4 bases) -> 4 ASCII bytes.
+__device__ __forceinline__ u32 expand4(u32 p) {
+    u32 x = (p | (p << 4)) & 0x0F0Fu;
+    x = (x | (x << 2)) & 0x3333u;           // code k in nibble k
+    return __byte_perm(0x47544341u, 0u, x); // "ACTG"[code]
+}
+
+__device__ __forceinline__ void deposit64(u32 *stream, int64_t bit, u64 w) {
+    int wi = (int)(bit >> 5);
+    u32 sh = (u32)bit & 31;
+    u32 lo = (u32)w, hi = (u32)(w >> 32);
+    u32 a = lo << sh;
+    u32 b = __funnelshift_l(lo, hi, sh);
+    u32 c = sh ? hi >> (32 - sh) : 0u;
+    if (a) atomicOr(&stream[wi], a);
+    if (b) atomicOr(&stream[wi + 1], b);
+    if (c) atomicOr(&stream[wi + 2], c);
+}
+
+// Expand stream[] (covering output bytes from index a0, chunk c = 16 bytes) into out[t0, t1).
+template <int THREADS>
+__device__ __forceinline__ void store_tile(uint8_t *out, int64_t a0, int64_t t0, int64_t t1, const u32 *stream) {
+    const int nchunks = (int)((t1 - a0 + 15) >> 4);
+    for (int c = threadIdx.x; c < nchunks; c += THREADS) {
+        u32 s = stream[c];
+        uint4 v = make_uint4(expand4(s & 0xFF), expand4((s >> 8) & 0xFF), expand4((s >> 16) & 0xFF), expand4(s >> 24));
+        int64_t idx = a0 + 16 * (int64_t)c;
+        if (idx >= t0 && idx + 16 <= t1) {
+            *reinterpret_cast<uint4 *>(out + idx) = v;
+        } else {
+            u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                int64_t j = idx + b;
+                if (j >= t0 && j < t1) out[j] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+            }
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) decode_fixed_kernel(const u64 *words, const uint8_t *lens, int64_t n,
+                                                                const int64_t *out_off, uint8_t *out) {
+    constexpr int MAXLEN = 32 * W;
+    constexpr int MAX_CHUNKS = (kThreads * MAXLEN + 30) / 16 + 1;
+    __shared__ u32 stream[MAX_CHUNKS + 3];
+    const int64_t mis = (int64_t)((uintptr_t)out & 15);
+    const int64_t ntiles = (n + kThreads - 1) / kThreads;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kThreads;
+        const int nreads = (int)min((int64_t)kThreads, n - first);
+        const int64_t t0 = out_off[first], t1 = out_off[first + nreads];
+        if (t1 < t0 || t1 - t0 > (int64_t)kThreads * MAXLEN) continue;   // inconsistent offsets: nothing sane to write
+        const int64_t a0 = ((t0 + mis) & ~(int64_t)15) - mis;
+        const int nchunks = (int)((t1 - a0 + 15) >> 4);
+        for (int c = threadIdx.x; c < nchunks + 3; c += kThreads) stream[c] = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < nreads) {
+            const int64_t i = first + threadIdx.x;
+            const int len = min((int)lens[i], MAXLEN);
+            const int64_t o0 = out_off[i];
+            if (o0 >= t0 && o0 + len <= t1) {
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    int nb = 2 * len - 64 * k;
+                    if (nb > 0) {
+                        u64 w = words[(size_t)i * W + k];
+                        if (nb < 64) w &= (1ull << nb) - 1;
+                        deposit64(stream, 2 * (o0 - a0) + 64 * k, w);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        store_tile<kThreads>(out, a0, t0, t1, stream);
+        __syncthreads();
+    }
+}
+
+constexpr int kVarTileReads = 32;
+constexpr int kVarMaxChunks = (kVarTileReads * 1024 + 30) / 16 + 1;
+
+__global__ void __launch_bounds__(kThreads) decode_var_kernel(const u64 *words, const int64_t *word_off,
+                                                              const uint16_t *lens, int64_t n, const int64_t *out_off,
+                                                              uint8_t *out) {
+    __shared__ u32 stream[kVarMaxChunks + 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t mis = (int64_t)((uintptr_t)out & 15);
+    const int64_t ntiles = (n + kVarTileReads - 1) / kVarTileReads;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kVarTileReads;
+        const int nreads = (int)min((int64_t)kVarTileReads, n - first);
+        const int64_t t0 = out_off[first], t1 = out_off[first + nreads];
+        if (t1 < t0 || t1 - t0 > (int64_t)kVarTileReads * 1024) continue;
+        const int64_t a0 = ((t0 + mis) & ~(int64_t)15) - mis;
+        const int nchunks = (int)((t1 - a0 + 15) >> 4);
+        for (int c = threadIdx.x; c < nchunks + 3; c += kThreads) stream[c] = 0;
+        __syncthreads();
+        for (int r = warp; r < nreads; r += kThreads / 32) {
+            const int64_t i = first + r;
+            const int len = min((int)lens[i], 1024);
+            const int64_t o0 = out_off[i];
+            const int nb = 2 * len - 64 * lane;
+            if (nb > 0 && o0 >= t0 && o0 + len <= t1) {
+                u64 w = words[word_off[i] + lane];
+                if (nb < 64) w &= (1ull << nb) - 1;
+                deposit64(stream, 2 * (o0 - a0) + 64 * lane, w);
+            }
+        }
+        __syncthreads();
+        store_tile<kThreads>(out, a0, t0, t1, stream);
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// Hamming distance.  Replaces __xor__ (short_seq_64.pyx:77-84, short_seq_192.pyx:74-91,
+// short_seq_var.pyx:64-81).  Canonical packed words keep bits beyond 2*len zero,
+// so whole-word popcounts equal the reference's sum over ceil(len/32) blocks.
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads) hamming64_kernel(const u64 *a, const uint8_t *la, const u64 *b,
+                                                             const uint8_t *lb, int64_t n, uint8_t *dist, DevReport *rep) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        int d = diff_bases(a[i], b[i]);
+        if (la[i] != lb[i]) { atomicMin(&rep->first_len_mismatch, (u64)i); d = 0xFF; }
+        dist[i] = (uint8_t)d;
+    }
+}
+
+// 3 words per read: the flat word arrays are swept coalesced, per-word differences go through
+// shared memory and one thread per read adds its three.
+__global__ void __launch_bounds__(kThreads) hamming192_kernel(const u64 *a, const uint8_t *la, const u64 *b,
+                                                              const uint8_t *lb, int64_t n, uint8_t *dist, DevReport *rep) {
+    __shared__ uint8_t d[3 * kThreads];
+    const int64_t ntiles = (n + kThreads - 1) / kThreads;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kThreads;
+        const int nreads = (int)min((int64_t)kThreads, n - first);
+        for (int k = threadIdx.x; k < 3 * nreads; k += kThreads)
+            d[k] = (uint8_t)diff_bases(a[3 * first + k], b[3 * first + k]);
+        __syncthreads();
+        if ((int)threadIdx.x < nreads) {
+            const int64_t i = first + threadIdx.x;
+            int s = d[3 * threadIdx.x] + d[3 * threadIdx.x + 1] + d[3 * threadIdx.x + 2];
+            if (la[i] != lb[i]) { atomicMin(&rep->first_len_mismatch, (u64)i); s = 0xFF; }
+            dist[i] = (uint8_t)s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) hammingvar_kernel(const u64 *a, const int64_t *aoff, const uint16_t *la,
+                                                              const u64 *b, const int64_t *boff, const uint16_t *lb,
+                                                              int64_t n, uint16_t *dist, DevReport *rep) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int len = la[i];
+        int d = 0;
+        if (len != lb[i]) {
+            if (lane == 0) { atomicMin(&rep->first_len_mismatch, (u64)i); dist[i] = 0xFFFF; }
+            continue;
+        }
+        const int nw = (len + 31) >> 5;
+        if (lane < nw) d = diff_bases(a[aoff[i] + lane], b[boff[i] + lane]);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, s);
+        if (lane == 0) dist[i] = (uint16_t)d;
+    }
+}
+
+// Query x reference set.  The refs (words + lengths) are staged in shared memory in chunks;
+// every thread owns one query and scans the chunk.
+constexpr int kRefChunk = 1024;
+template <int W>
+__global__ void __launch_bounds__(kThreads) refset_kernel(const u64 *q, const uint8_t *lq, int64_t nq, const u64 *refs,
+                                                          const uint8_t *lr, int nr, int thresh, uint8_t *min_dist,
+                                                          u32 *argmin, u32 *n_within) {
+    __shared__ u64 s_ref[kRefChunk * W];
+    __shared__ uint8_t s_len[kRefChunk];
+    const int64_t ntiles = (nq + kThreads - 1) / kThreads;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i = tile * kThreads + threadIdx.x;
+        const bool mine = i < nq;
+        u64 qw[W];
+        int qlen = -1;
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < W; k++) qw[k] = q[(size_t)i * W + k];
+            qlen = lq[i];
+        }
+        int best = 255, within = 0;
+        u32 best_j = 0xFFFFFFFFu;
+        for (int r0 = 0; r0 < nr; r0 += kRefChunk) {
+            const int cnt = min(kRefChunk, nr - r0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < cnt * W; k += kThreads) s_ref[k] = refs[(size_t)r0 * W + k];
+            for (int k = threadIdx.x; k < cnt; k += kThreads) s_len[k] = lr[r0 + k];
+            __syncthreads();
+            if (mine) {
+                for (int j = 0; j < cnt; j++) {
+                    if (s_len[j] != qlen) continue;
+                    int d = 0;
+#pragma unroll
+                    for (int k = 0; k < W; k++) d += diff_bases(qw[k], s_ref[j * W + k]);
+                    if (d < best) { best = d; best_j = (u32)(r0 + j); }
+                    within += d <= thresh ? 1 : 0;
+                }
+            }
+        }
+        if (mine) {
+            min_dist[i] = (uint8_t)best;
+            argmin[i] = best_j;
+            if (n_within) n_within[i] = (u32)within;
+        }
+    }
+}
+
+// =============================================================================================
+// Synthetic reads (measurement tooling; same generator as oracle/ssq_oracle.c).
+// =============================================================================================
+__device__ __forceinline__ u64 synth_key(u64 seed, int64_t i, int64_t n_keys) { return mix64(seed + (u64)i) % (u64)n_keys; }
+
+// One thread per (read, 32-base block).
+__global__ void __launch_bounds__(kThreads) synth_fill_kernel(u64 seed, int64_t first_read, int64_t n, int64_t n_keys,
+                                                              int blocks_per_read, const int64_t *offsets, uint8_t *ascii) {
+    const int64_t total = n * blocks_per_read;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = t / blocks_per_read;
+        const int blk = (int)(t - i * blocks_per_read);
+        const int64_t o0 = offsets[i];
+        const int len = (int)(offsets[i + 1] - o0);
+        const int nb = min(32, len - 32 * blk);
+        if (nb <= 0) continue;
+        const u64 key = synth_key(seed, first_read + i, n_keys);
+        u64 r = mix64(seed + 0x5EED0002ull + key * 32ull + (u64)blk);
+        uint8_t *dst = ascii + o0 + 32 * blk;
+        if (nb == 32 && (((uintptr_t)dst) & 15) == 0) {
+            u32 w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                u32 p = (u32)(r >> (8 * k)) & 0xFF;
+                u32 x = (p | (p << 4)) & 0x0F0Fu;
+                x = (x | (x << 2)) & 0x3333u;
+                w[k] = __byte_perm(0x54474341u, 0u, x);   // "ACGT"[code]
+            }
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            for (int j = 0; j < nb; j++) dst[j] = (uint8_t)"ACGT"[(r >> (2 * j)) & 3];
+        }
+    }
+}
+
+__global__ void synth_fixed_offsets_kernel(int64_t n, int64_t len, int64_t *offsets) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x)
+        offsets[i] = i * len;
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+extern "C" {
+
+int ssq_decode64(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *out_offsets,
+                 uint8_t *ascii_out) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(words && lens && out_offsets && ascii_out, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    decode_fixed_kernel<1><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, out_offsets, ascii_out);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_decode192(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *out_offsets,
+                  uint8_t *ascii_out) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(words && lens && out_offsets && ascii_out, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    decode_fixed_kernel<3><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, out_offsets, ascii_out);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, const uint16_t *lens, int64_t n,
+                  const int64_t *out_offsets, uint8_t *ascii_out) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(words && word_off && lens && out_offsets && ascii_out, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, 4);
+    decode_var_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_hamming_pairs64(ssq_ctx *ctx, const uint64_t *a, const uint8_t *len_a, const uint64_t *b, const uint8_t *len_b,
+                        int64_t n, uint8_t *dist) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(a && b && len_a && len_b && dist, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    hamming64_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)a, len_a, (const u64 *)b, len_b, n, dist, ctx->d_report);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_hamming_pairs192(ssq_ctx *ctx, const uint64_t *a, const uint8_t *len_a, const uint64_t *b, const uint8_t *len_b,
+                         int64_t n, uint8_t *dist) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(a && b && len_a && len_b && dist, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    hamming192_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)a, len_a, (const u64 *)b, len_b, n, dist, ctx->d_report);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_hamming_pairsvar(ssq_ctx *ctx, const uint64_t *a, const int64_t *a_off, const uint16_t *len_a, const uint64_t *b,
+                         const int64_t *b_off, const uint16_t *len_b, int64_t n, uint16_t *dist) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    if (n == 0) return SSQ_OK;
+    SSQ_ARG(a && b && a_off && b_off && len_a && len_b && dist, "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n * 32 + kThreads - 1) / kThreads, 8);
+    hammingvar_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)a, a_off, len_a, (const u64 *)b, b_off, len_b, n, dist,
+                                                          ctx->d_report);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_hamming_refset(ssq_ctx *ctx, int words_per_seq, const uint64_t *q, const uint8_t *len_q, int64_t nq,
+                       const uint64_t *refs, const uint8_t *len_r, int32_t nr, int32_t thresh, uint8_t *min_dist,
+                       uint32_t *argmin, uint32_t *n_within) {
+    SSQ_ARG(ctx != nullptr && nq >= 0 && nr >= 0, "bad ctx / sizes");
+    SSQ_ARG(words_per_seq == 1 || words_per_seq == 3, "words_per_seq must be 1 or 3");
+    if (nq == 0) return SSQ_OK;
+    SSQ_ARG(q && len_q && min_dist && argmin && (nr == 0 || (refs && len_r)), "NULL buffer");
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (nq + kThreads - 1) / kThreads, 4);
+    if (words_per_seq == 1)
+        refset_kernel<1><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)q, len_q, nq, (const u64 *)refs, len_r, nr, thresh,
+                                                             min_dist, argmin, n_within);
+    else
+        refset_kernel<3><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)q, len_q, nq, (const u64 *)refs, len_r, nr, thresh,
+                                                             min_dist, argmin, n_within);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_synth_reads(ssq_ctx *ctx, uint64_t seed, int64_t first_read, int64_t n, int64_t n_keys, int32_t len_lo,
+                    int32_t len_hi, int64_t *offsets, uint8_t *ascii) {
+    SSQ_ARG(ctx != nullptr && n >= 0 && n_keys > 0, "bad ctx / sizes");
+    SSQ_ARG(len_lo >= 0 && len_hi >= len_lo && len_hi <= 1024, "bad length range");
+    SSQ_ARG(offsets != nullptr && (ascii != nullptr || n == 0 || len_hi == 0), "NULL buffer");
+    DeviceGuard g(ctx->device);
+    if (len_lo == len_hi) {
+        synth_fixed_offsets_kernel<<<grid_for(ctx, (n + 1 + 255) / 256, 8), 256, 0, ctx->stream>>>(n, len_lo, offsets);
+        SSQ_LAUNCH_CHECK();
+    } else {
+        int rc = scan_synth_lens(ctx, seed, first_read, n, n_keys, len_lo, len_hi, offsets);
+        if (rc) return rc;
+    }
+    if (n == 0 || len_hi == 0) return SSQ_OK;
+    const int bpr = (len_hi + 31) / 32;
+    int grid = grid_for(ctx, (n * bpr + kThreads - 1) / kThreads, 8);
+    synth_fill_kernel<<<grid, kThreads, 0, ctx->stream>>>(seed, first_read, n, n_keys, bpr, offsets, ascii);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+// ssq_counter.cu -- the dedup counter: a device hash table of (length, words) -> count.
+//
+// Replaces ShortSeqCounter (reference counter.pyx:10-54).  See ssq_table.cuh for the slot
+// formats.  Host-side policy in this file:
+//   * capacity is a power of two >= 2 x expected_unique (min 2^16 slots);
+//   * a batch is enqueued as sub-batches of cap/8 reads, each preceded by a one-thread
+//     "gate" kernel that sets a stop flag when the table could exceed 75 % load during the
+//     sub-batch; kernels behind a raised flag do nothing.  The host synchronises once per
+//     batch, and only if the flag was raised grows the table (x4, rehash on the device) and
+//     resumes from the stopped sub-batch -- so a well-sized table costs no extra syncs and an
+//     undersized one is still exact.
+#include "ssq_internal.h"
+#include "ssq_table.cuh"
+
+namespace ssq {
+
+int launch_pack_count(ssq_ctx *ctx, int klass, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets,
+                      int64_t n, int64_t index_base, u64 *words, uint8_t *lens, const TableView &t, const u64 *stop);
+
+constexpr int kThreads = 256;
+
+// gate[0] = stop flag, gate[1] = index of the first stopped sub-batch
+__global__ void gate_kernel(u64 *gate, const u64 *size, u64 incoming, u64 limit, u64 batch_index) {
+    if (gate[0] == 0 && *size + incoming > limit) { gate[0] = 1; gate[1] = batch_index; }
+}
+
+__device__ __forceinline__ void block_add_new(const TableView &t, u32 my_new, u32 *s_new) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+    if ((threadIdx.x & 31) == 0) s_new[threadIdx.x >> 5] = my_new;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 tot = 0;
+        for (int k = 0; k < kThreads / 32; k++) tot += s_new[k];
+        if (tot) atomicAdd(t.size, tot);
+    }
+}
+
+__device__ __forceinline__ bool len_in_class(int klass, u32 len) {
+    return klass == SSQ_CLASS_64 ? len <= 32 : (len >= 33 && len <= 96);
+}
+
+// Insert packed keys; counts == nullptr means weight 1.
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) insert_kernel(TableView t, const u64 *words, const uint8_t *lens,
+                                                          const u64 *counts, int64_t n, int64_t index_base,
+                                                          const u64 *stop) {
+    __shared__ u32 s_new[kThreads / 32];
+    if (stop != nullptr && *stop != 0) return;
+    u32 my_new = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        u32 len = lens[i];
+        u64 add = counts ? counts[i] : 1ull;
+        bool is_new = false;
+        if (!len_in_class(KLASS, len)) {
+            atomicMin(&t.rep->first_bad_len, (u64)(index_base + i));
+        } else if (add != 0) {
+            if constexpr (KLASS == SSQ_CLASS_64) insert64(t, words[i], len, add, is_new);
+            else insert192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], len, add, is_new);
+        }
+        my_new += is_new ? 1u : 0u;
+    }
+    block_add_new(t, my_new, s_new);
+}
+
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) lookup_kernel(TableView t, const u64 *words, const uint8_t *lens, int64_t n,
+                                                          u64 *counts) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        u32 len = lens[i];
+        u64 c = 0;
+        if (len_in_class(KLASS, len)) {
+            if constexpr (KLASS == SSQ_CLASS_64) {
+                u64 s = find64(t, words[i], len);
+                if (s != kNoIndex) c = ld_relaxed_u64(t.slots + 2 * s + 1);
+            } else {
+                u64 s = find192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], len);
+                if (s != kNoIndex) c = ld_relaxed_u64(t.slots + 4 * s) >> 8;
+            }
+        }
+        counts[i] = c;
+    }
+}
+
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) first_index_kernel(TableView t, const u64 *words, const uint8_t *lens,
+                                                               int64_t n, int64_t base_index) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        u32 len = lens[i];
+        if (!len_in_class(KLASS, len)) continue;
+        u64 s;
+        if constexpr (KLASS == SSQ_CLASS_64) s = find64(t, words[i], len);
+        else s = find192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], len);
+        if (s != kNoIndex) red_min_u64(t.first_idx + s, (u64)(base_index + i));
+    }
+}
+
+// Re-insert every occupied slot of `src` into `dst` (growth).
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) rehash_kernel(TableView src, TableView dst) {
+    __shared__ u32 s_new[kThreads / 32];
+    const u64 cap = 1ull << src.log2_cap;
+    u32 my_new = 0;
+    for (u64 s = (u64)blockIdx.x * kThreads + threadIdx.x; s < cap; s += (u64)gridDim.x * kThreads) {
+        bool is_new = false;
+        u64 ds = kNoIndex;
+        if constexpr (KLASS == SSQ_CLASS_64) {
+            u64 key = src.slots[2 * s];
+            if (key != 0) {
+                u32 len;
+                u64 h2 = slot64_h2(src, s, key, len);
+                ds = insert64_hashed(dst, h2, key, src.slots[2 * s + 1], is_new);
+            }
+        } else {
+            u64 meta = src.slots[4 * s];
+            if ((meta & 0xFF) != 0)
+                ds = insert192(dst, src.slots[4 * s + 1], src.slots[4 * s + 2], src.slots[4 * s + 3],
+                               (u32)(meta & 0xFF) + 32, meta >> 8, is_new);
+        }
+        if (ds != kNoIndex && src.first_idx != nullptr) dst.first_idx[ds] = src.first_idx[s];
+        my_new += is_new ? 1u : 0u;
+    }
+    block_add_new(dst, my_new, s_new);
+}
+
+// ---- export ---------------------------------------------------------------------------------
+constexpr int kExportItems = 8;    // slots per thread
+constexpr int kMaxParts = 256;
+
+struct Tuple {
+    u64 w0, w1, w2, count, first;
+    u32 len, part;
+    bool used;
+};
+
+template <int KLASS>
+__device__ __forceinline__ Tuple read_slot(const TableView &t, u64 s, int log2_parts) {
+    Tuple r;
+    r.used = false;
+    r.w1 = r.w2 = 0;
+    u64 h;
+    if constexpr (KLASS == SSQ_CLASS_64) {
+        u64 key = t.slots[2 * s];
+        if (key == 0) return r;
+        u64 h2 = slot64_h2(t, s, key, r.len);
+        h = rotr64(h2, t.rot);
+        r.w0 = unmix64(h);
+        r.count = t.slots[2 * s + 1];
+    } else {
+        u64 meta = t.slots[4 * s];
+        if ((meta & 0xFF) == 0) return r;
+        r.len = (u32)(meta & 0xFF) + 32;
+        r.count = meta >> 8;
+        r.w0 = t.slots[4 * s + 1]; r.w1 = t.slots[4 * s + 2]; r.w2 = t.slots[4 * s + 3];
+        h = hash192(r.w0, r.w1, r.w2, r.len);
+    }
+    r.first = t.first_idx ? t.first_idx[s] : kNoIndex;
+    r.part = log2_parts ? (u32)(h >> (64 - log2_parts)) : 0u;
+    r.used = true;
+    return r;
+}
+
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) export_count_kernel(TableView t, int log2_parts, u64 *part_counts) {
+    __shared__ u32 cnt[kMaxParts];
+    for (int p = threadIdx.x; p < kMaxParts; p += kThreads) cnt[p] = 0;
+    __syncthreads();
+    const u64 cap = 1ull << t.log2_cap;
+    for (u64 s = (u64)blockIdx.x * kThreads + threadIdx.x; s < cap; s += (u64)gridDim.x * kThreads) {
+        Tuple r = read_slot<KLASS>(t, s, log2_parts);
+        if (r.used) atomicAdd(&cnt[r.part], 1u);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < (1 << log2_parts); p += kThreads)
+        if (cnt[p]) atomicAdd(&part_counts[p], (u64)cnt[p]);
+}
+
+// cursors[p] = exclusive scan of part_counts: where partition p starts in the output
+__global__ void export_bases_kernel(const u64 *part_counts, u64 *cursors, int nparts) {
+    u64 run = 0;
+    for (int p = 0; p < nparts; p++) { cursors[p] = run; run += part_counts[p]; }
+}
+
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, int log2_parts,
+                                                                  u64 *cursors, u64 *words, uint8_t *lens, u64 *counts,
+                                                                  int64_t *first_idx) {
+    __shared__ u32 cnt[kMaxParts];
+    __shared__ u64 base[kMaxParts];
+    const int nparts = 1 << log2_parts;
+    const u64 cap = 1ull << t.log2_cap;
+    const u64 tile = (u64)kThreads * kExportItems;
+    for (u64 tile0 = (u64)blockIdx.x * tile; tile0 < cap; tile0 += (u64)gridDim.x * tile) {
+        for (int p = threadIdx.x; p < nparts; p += kThreads) cnt[p] = 0;
+        __syncthreads();
+        Tuple r[kExportItems];
+        u32 rank[kExportItems];
+#pragma unroll
+        for (int k = 0; k < kExportItems; k++) {
+            u64 s = tile0 + (u64)k * kThreads + threadIdx.x;
+            r[k].used = false;
+            if (s < cap) r[k] = read_slot<KLASS>(t, s, log2_parts);
+            if (r[k].used) rank[k] = atomicAdd(&cnt[r[k].part], 1u);
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < nparts; p += kThreads)
+            base[p] = cnt[p] ? atomicAdd(&cursors[p], (u64)cnt[p]) : 0;   // cursors start at the partition bases
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kExportItems; k++) {
+            if (!r[k].used) continue;
+            u64 o = base[r[k].part] + rank[k];
+            if constexpr (KLASS == SSQ_CLASS_64) words[o] = r[k].w0;
+            else { words[3 * o] = r[k].w0; words[3 * o + 1] = r[k].w1; words[3 * o + 2] = r[k].w2; }
+            lens[o] = (uint8_t)r[k].len;
+            counts[o] = r[k].count;
+            if (first_idx) first_idx[o] = (int64_t)r[k].first;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void fill_u64_kernel(u64 *p, u64 v, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static size_t slot_bytes(int klass) { return klass == SSQ_CLASS_64 ? 16 : 32; }
+
+static TableView view_of(const ssq_counter *c) {
+    TableView t;
+    t.slots = (u64 *)c->slots;
+    t.first_idx = c->first_idx;
+    t.size = c->d_size;
+    t.rep = c->ctx->d_report;
+    t.log2_cap = c->log2_cap;
+    t.rot = c->hash_rot;
+    return t;
+}
+
+static int log2_cap_for(int64_t expected_unique) {
+    int l = kMinLog2Cap;
+    while (l < 40 && (1ll << l) < 2 * expected_unique) l++;
+    return l;
+}
+
+// Grow to 2^new_log2 slots, rehashing on the device.  The stream is idle on entry and on exit.
+static int grow(ssq_counter *c, int new_log2) {
+    ssq_ctx *ctx = c->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t nslots = (size_t)1 << new_log2;
+    void *nslots_p = nullptr;
+    u64 *nfirst = nullptr;
+    SSQ_CUDA(cudaMalloc(&nslots_p, nslots * slot_bytes(c->klass)));
+    SSQ_CUDA(cudaMemsetAsync(nslots_p, 0, nslots * slot_bytes(c->klass), st));
+    if (c->first_idx) {
+        SSQ_CUDA(cudaMalloc(&nfirst, nslots * sizeof(u64)));
+        SSQ_CUDA(cudaMemsetAsync(nfirst, 0xFF, nslots * sizeof(u64), st));
+    }
+    TableView src = view_of(c);
+    TableView dst = src;
+    dst.slots = (u64 *)nslots_p;
+    dst.first_idx = nfirst;
+    dst.log2_cap = new_log2;
+    SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), st));
+    int grid = grid_for(ctx, ((int64_t)1 << c->log2_cap) / kThreads, 8);
+    if (c->klass == SSQ_CLASS_64) rehash_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, st>>>(src, dst);
+    else rehash_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, st>>>(src, dst);
+    SSQ_LAUNCH_CHECK();
+    SSQ_CUDA(cudaStreamSynchronize(st));
+    SSQ_CUDA(cudaFree(c->slots));
+    if (c->first_idx) SSQ_CUDA(cudaFree(c->first_idx));
+    c->slots = nslots_p;
+    c->first_idx = nfirst;
+    c->log2_cap = new_log2;
+    return SSQ_OK;
+}
+
+// Runs launch(start, count, stop_flag) over [0, n) in gated sub-batches; grows and resumes when stopped.
+template <class Launch>
+static int run_gated(ssq_counter *c, int64_t n, Launch launch) {
+    ssq_ctx *ctx = c->ctx;
+    cudaStream_t st = ctx->stream;
+    int64_t pos = 0;
+    while (pos < n) {
+        const int64_t cap = (int64_t)1 << c->log2_cap;
+        const int64_t sub = cap / 8;
+        const u64 limit = (u64)(cap - cap / 4);
+        SSQ_CUDA(cudaMemsetAsync(c->d_gate, 0, 2 * sizeof(u64), st));
+        int64_t k = 0;
+        for (int64_t p = pos; p < n; p += sub, k++) {
+            int64_t cnt = n - p < sub ? n - p : sub;
+            gate_kernel<<<1, 1, 0, st>>>(c->d_gate, c->d_size, (u64)cnt, limit, (u64)k);
+            SSQ_LAUNCH_CHECK();
+            int rc = launch(p, cnt, c->d_gate);
+            if (rc) return rc;
+        }
+        SSQ_CUDA(cudaMemcpyAsync(c->h_gate, c->d_gate, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        SSQ_CUDA(cudaStreamSynchronize(st));
+        if (c->h_gate[0] == 0) break;
+        pos += (int64_t)c->h_gate[1] * sub;
+        // room for what is there plus the rest of this batch, at least x4
+        int want = log2_cap_for((int64_t)*c->h_size + (n - pos < 4 * cap ? n - pos : 4 * cap));
+        if (want < c->log2_cap + 2) want = c->log2_cap + 2;
+        int rc = grow(c, want);
+        if (rc) return rc;
+    }
+    return SSQ_OK;
+}
+
+// Fused pack+count of reads whose bytes are ascii[lo, hi) (ascii may be a virtual base pointer);
+// index_base is added to the read indices that data errors are reported with.
+int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets, int64_t n,
+                    int64_t index_base, u64 *words, uint8_t *lens) {
+    ssq_ctx *ctx = c->ctx;
+    const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
+    return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
+        return launch_pack_count(ctx, c->klass, ascii, lo, hi, offsets + p, cnt, index_base + p, words + (size_t)p * W,
+                                 lens + p, view_of(c), stop);
+    });
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+extern "C" {
+
+int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int hash_rot, ssq_counter **out) {
+    SSQ_ARG(ctx != nullptr && out != nullptr, "NULL argument");
+    SSQ_ARG(klass == SSQ_CLASS_64 || klass == SSQ_CLASS_192, "klass must be SSQ_CLASS_64 or SSQ_CLASS_192");
+    SSQ_ARG(hash_rot >= 0 && hash_rot <= 56, "hash_rot out of range");
+    SSQ_ARG(expected_unique >= 0, "expected_unique < 0");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    ssq_counter *c = new ssq_counter();
+    c->ctx = ctx;
+    c->klass = klass;
+    c->hash_rot = hash_rot;
+    c->log2_cap = log2_cap_for(expected_unique);
+    c->slots = nullptr;
+    c->first_idx = nullptr;
+    const size_t bytes = ((size_t)1 << c->log2_cap) * slot_bytes(klass);
+    SSQ_CUDA(cudaMalloc(&c->slots, bytes));
+    SSQ_CUDA(cudaMalloc(&c->d_size, 4 * sizeof(u64)));
+    c->d_gate = c->d_size + 1;
+    SSQ_CUDA(cudaHostAlloc(&c->h_size, 4 * sizeof(u64), cudaHostAllocDefault));
+    c->h_gate = c->h_size + 1;
+    SSQ_CUDA(cudaMemsetAsync(c->slots, 0, bytes, ctx->stream));
+    SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, 4 * sizeof(u64), ctx->stream));
+    *out = c;
+    return SSQ_OK;
+}
+
+int ssq_counter_destroy(ssq_counter *c) {
+    if (!c) return SSQ_OK;
+    DeviceGuard g(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaFree(c->slots);
+    cudaFree(c->first_idx);
+    cudaFree(c->d_size);
+    cudaFreeHost(c->h_size);
+    delete c;
+    return SSQ_OK;
+}
+
+int ssq_counter_clear(ssq_counter *c) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    DeviceGuard g(c->ctx->device);
+    const size_t nslots = (size_t)1 << c->log2_cap;
+    SSQ_CUDA(cudaMemsetAsync(c->slots, 0, nslots * slot_bytes(c->klass), c->ctx->stream));
+    SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), c->ctx->stream));
+    if (c->first_idx) SSQ_CUDA(cudaMemsetAsync(c->first_idx, 0xFF, nslots * sizeof(u64), c->ctx->stream));
+    return SSQ_OK;
+}
+
+static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts, int64_t n) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    SSQ_ARG(n >= 0 && (n == 0 || (words != nullptr && lens != nullptr)), "bad batch");
+    if (n == 0) return SSQ_OK;
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
+    return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
+        TableView t = view_of(c);
+        int grid = grid_for(ctx, (cnt + kThreads - 1) / kThreads, 8);
+        const u64 *w = (const u64 *)words + (size_t)p * W;
+        const u64 *cn = counts ? (const u64 *)counts + p : nullptr;
+        if (c->klass == SSQ_CLASS_64)
+            insert_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, w, lens + p, cn, cnt, p, stop);
+        else
+            insert_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, w, lens + p, cn, cnt, p, stop);
+        SSQ_LAUNCH_CHECK();
+        return SSQ_OK;
+    });
+}
+
+int ssq_counter_insert(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n) {
+    return insert_common(c, words, lens, nullptr, n);
+}
+
+int ssq_counter_merge(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts, int64_t n) {
+    SSQ_ARG(n == 0 || counts != nullptr, "counts is NULL");
+    return insert_common(c, words, lens, counts, n);
+}
+
+int ssq_counter_pack_count(ssq_counter *c, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,
+                           int64_t n, uint64_t *words, uint8_t *lens) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    SSQ_ARG(n >= 0 && ascii_bytes >= 0, "negative size");
+    SSQ_ARG(n == 0 || (offsets != nullptr && words != nullptr && lens != nullptr), "NULL buffer");
+    if (n == 0) return SSQ_OK;
+    DeviceGuard g(c->ctx->device);
+    return pack_count_impl(c, ascii, 0, ascii_bytes, offsets, n, 0, (u64 *)words, lens);
+}
+
+int ssq_counter_first_index(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n, int64_t base_index) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    SSQ_ARG(n >= 0 && (n == 0 || (words != nullptr && lens != nullptr)), "bad batch");
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    if (!c->first_idx) {
+        const size_t nslots = (size_t)1 << c->log2_cap;
+        SSQ_CUDA(cudaMalloc(&c->first_idx, nslots * sizeof(u64)));
+        SSQ_CUDA(cudaMemsetAsync(c->first_idx, 0xFF, nslots * sizeof(u64), ctx->stream));
+    }
+    if (n == 0) return SSQ_OK;
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    TableView t = view_of(c);
+    if (c->klass == SSQ_CLASS_64)
+        first_index_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index);
+    else
+        first_index_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_counter_lookup(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n, uint64_t *counts) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    SSQ_ARG(n >= 0 && (n == 0 || (words != nullptr && lens != nullptr && counts != nullptr)), "bad batch");
+    if (n == 0) return SSQ_OK;
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    TableView t = view_of(c);
+    if (c->klass == SSQ_CLASS_64)
+        lookup_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, (u64 *)counts);
+    else
+        lookup_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, (u64 *)counts);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_counter_size(ssq_counter *c, int64_t *n_unique) {
+    SSQ_ARG(c != nullptr && n_unique != nullptr, "NULL argument");
+    DeviceGuard g(c->ctx->device);
+    SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, c->ctx->stream));
+    SSQ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    *n_unique = (int64_t)*c->h_size;
+    return SSQ_OK;
+}
+
+int ssq_counter_capacity(ssq_counter *c, int64_t *slots) {
+    SSQ_ARG(c != nullptr && slots != nullptr, "NULL argument");
+    *slots = (int64_t)1 << c->log2_cap;
+    return SSQ_OK;
+}
+
+int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *lens, uint64_t *counts,
+                       int64_t *first_idx, int64_t *part_counts) {
+    SSQ_ARG(c != nullptr, "counter is NULL");
+    SSQ_ARG(n_parts >= 1 && n_parts <= kMaxParts && (n_parts & (n_parts - 1)) == 0, "n_parts must be a power of two <= 256");
+    SSQ_ARG(words != nullptr && lens != nullptr && counts != nullptr && part_counts != nullptr, "NULL buffer");
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    u64 *cursors = nullptr;
+    SSQ_CUDA(cudaMallocAsync(&cursors, kMaxParts * sizeof(u64), st));
+    SSQ_CUDA(cudaMemsetAsync(part_counts, 0, n_parts * sizeof(u64), st));
+    TableView t = view_of(c);
+    const int64_t cap = (int64_t)1 << c->log2_cap;
+    int grid1 = grid_for(ctx, cap / kThreads, 8);
+    int grid2 = grid_for(ctx, cap / (kThreads * kExportItems), 4);
+    if (c->klass == SSQ_CLASS_64) {
+        export_count_kernel<SSQ_CLASS_64><<<grid1, kThreads, 0, st>>>(t, log2_parts, (u64 *)part_counts);
+        export_bases_kernel<<<1, 1, 0, st>>>((const u64 *)part_counts, cursors, n_parts);
+        export_scatter_kernel<SSQ_CLASS_64><<<grid2, kThreads, 0, st>>>(t, log2_parts, cursors, (u64 *)words, lens,
+                                                                        (u64 *)counts, first_idx);
+    } else {
+        export_count_kernel<SSQ_CLASS_192><<<grid1, kThreads, 0, st>>>(t, log2_parts, (u64 *)part_counts);
+        export_bases_kernel<<<1, 1, 0, st>>>((const u64 *)part_counts, cursors, n_parts);
+        export_scatter_kernel<SSQ_CLASS_192><<<grid2, kThreads, 0, st>>>(t, log2_parts, cursors, (u64 *)words, lens,
+                                                                         (u64 *)counts, first_idx);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(cursors, st);
+    if (e != cudaSuccess) return cuda_fail(e, "export kernels", __FILE__, __LINE__);
+    return SSQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// ssq_ctx.cu -- contexts, error plumbing and memory helpers of the C ABI.
+#include <stdarg.h>
+#include <string.h>
+#include "ssq_internal.h"
+
+namespace ssq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();  // clear the sticky-less error state
+    return SSQ_ERR_CUDA;
+}
+
+__global__ void reset_report_kernel(DevReport *r) {
+    r->first_bad_base = kNoIndex;
+    r->first_bad_len = kNoIndex;
+    r->first_too_long = kNoIndex;
+    r->first_len_mismatch = kNoIndex;
+    r->table_overflow = 0;
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+extern "C" {
+
+int ssq_abi_version(void) { return SSQ_ABI_VERSION; }
+
+const char *ssq_last_error(void) { return g_err; }
+
+int ssq_device_count(int *count) {
+    SSQ_ARG(count != nullptr, "count is NULL");
+    *count = 0;
+    SSQ_CUDA(cudaGetDeviceCount(count));
+    return SSQ_OK;
+}
+
+int ssq_ctx_create(int device, ssq_ctx **out) {
+    SSQ_ARG(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    SSQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) { set_error("no CUDA device (there is no CPU fallback)"); return SSQ_ERR_CUDA; }
+    SSQ_ARG(device >= 0 && device < ndev, "device index out of range");
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    SSQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return SSQ_ERR_CUDA;
+    }
+    ssq_ctx *ctx = new ssq_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    SSQ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 2; i++) SSQ_CUDA(cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking));
+    SSQ_CUDA(cudaMalloc(&ctx->d_report, sizeof(DevReport)));
+    SSQ_CUDA(cudaHostAlloc(&ctx->h_report, sizeof(DevReport), cudaHostAllocDefault));
+    reset_report_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_report);
+    SSQ_LAUNCH_CHECK();
+    SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return SSQ_OK;
+}
+
+int ssq_ctx_destroy(ssq_ctx *ctx) {
+    if (!ctx) return SSQ_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_report);
+    cudaFreeHost(ctx->h_report);
+    for (int i = 0; i < 2; i++) cudaStreamDestroy(ctx->copy_streams[i]);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SSQ_OK;
+}
+
+int ssq_ctx_set_stream(ssq_ctx *ctx, void *cuda_stream) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SSQ_OK;
+}
+
+void *ssq_ctx_stream(ssq_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ssq_ctx_sync(ssq_ctx *ctx, ssq_report *report) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (report) { report->code = SSQ_OK; report->reserved = 0; report->first_bad_read = -1; }
+    SSQ_CUDA(cudaMemcpyAsync(ctx->h_report, ctx->d_report, sizeof(DevReport), cudaMemcpyDeviceToHost, ctx->stream));
+    reset_report_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_report);
+    SSQ_LAUNCH_CHECK();
+    SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const DevReport &r = *ctx->h_report;
+    // lowest failing read wins, like the reference's serial loop (counter.pyx:23-29)
+    u64 best = kNoIndex;
+    int code = SSQ_OK;
+    if (r.first_too_long < best) { best = r.first_too_long; code = SSQ_ERR_TOO_LONG; }
+    if (r.first_bad_len < best) { best = r.first_bad_len; code = SSQ_ERR_CLASS; }
+    if (r.first_bad_base < best) { best = r.first_bad_base; code = SSQ_ERR_BAD_BASE; }
+    if (r.first_len_mismatch < best) { best = r.first_len_mismatch; code = SSQ_ERR_LEN_MISMATCH; }
+    if (code == SSQ_OK && r.table_overflow != 0) { code = SSQ_ERR_TABLE_FULL; best = kNoIndex; }
+    if (report) {
+        report->code = code;
+        report->first_bad_read = best == kNoIndex ? -1 : (int64_t)best;
+    }
+    return SSQ_OK;
+}
+
+int ssq_malloc(ssq_ctx *ctx, size_t bytes, void **dptr) {
+    SSQ_ARG(ctx != nullptr && dptr != nullptr, "NULL argument");
+    DeviceGuard g(ctx->device);
+    *dptr = nullptr;
+    SSQ_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return SSQ_OK;
+}
+
+int ssq_free(ssq_ctx *ctx, void *dptr) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    SSQ_CUDA(cudaFree(dptr));
+    return SSQ_OK;
+}
+
+int ssq_host_alloc(size_t bytes, void **hptr) {
+    SSQ_ARG(hptr != nullptr, "hptr is NULL");
+    *hptr = nullptr;
+    SSQ_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SSQ_OK;
+}
+
+int ssq_host_free(void *hptr) {
+    SSQ_CUDA(cudaFreeHost(hptr));
+    return SSQ_OK;
+}
+
+int ssq_memcpy_h2d(ssq_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (bytes) SSQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SSQ_OK;
+}
+
+int ssq_memcpy_d2h(ssq_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (bytes) SSQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SSQ_OK;
+}
+
+int ssq_memset(ssq_ctx *ctx, void *dst, int value, size_t bytes) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (bytes) SSQ_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return SSQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// ssq_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssq {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u64 kNoIndex = 0xFFFFFFFFFFFFFFFFull;
+
+// Device-resident error record of a context.  Every field is an atomicMin /
+// atomicOr target; ssq_ctx_sync() copies it back and resets it.
+struct DevReport {
+    u64 first_bad_base;      // lowest read index with a non-ACGT byte
+    u64 first_bad_len;       // lowest read index whose length is outside the class (<= 1024)
+    u64 first_too_long;      // lowest read index longer than 1024
+    u64 first_len_mismatch;  // lowest pair index with len_a != len_b (Hamming)
+    u64 table_overflow;      // number of inserts that found no slot (counter unusable if != 0)
+    u64 pad[3];
+};
+
+// ---- hashing ---------------------------------------------------------------
+// splitmix64 finaliser: a bijection on 64-bit words, so a ShortSeq64 key can be
+// stored in the table as its hash and recovered on export.
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ u64 unmix64(u64 x) {
+    x ^= (x >> 31) ^ (x >> 62); x *= 0x319642B2D24D8EC3ull;
+    x ^= (x >> 27) ^ (x >> 54); x *= 0x96DE1B173F119089ull;
+    x ^= (x >> 30) ^ (x >> 60);
+    return x;
+}
+__host__ __device__ __forceinline__ u64 rotl64(u64 x, int r) { return r ? (x << r) | (x >> (64 - r)) : x; }
+__host__ __device__ __forceinline__ u64 rotr64(u64 x, int r) { return r ? (x >> r) | (x << (64 - r)) : x; }
+
+// Slot hash of a 3-word key (ShortSeq192).  Not a bijection; the key is stored verbatim.
+__host__ __device__ __forceinline__ u64 hash192(u64 w0, u64 w1, u64 w2, u32 len) {
+    u64 h = mix64(w2 ^ ((u64)len * 0x9E3779B97F4A7C15ull));
+    h = mix64(h ^ w1);
+    return mix64(h ^ w0);
+}
+
+// ---- memory intrinsics ---------------------------------------------------------
+// 16-byte streaming load that does not allocate in L1 (every input byte is read once).
+__device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// fire-and-forget add (RED): the result is never needed
+__device__ __forceinline__ void red_add_u64(u64 *p, u64 v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_u64(u64 *p, u64 v) {
+    asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// ---- 2-bit encoding -------------------------------------------------------------
+// Four ASCII bases in one 32-bit word -> 8 bits of 2-bit codes in the TOP byte
+// (code = (c>>1)&3: A0 C1 T2 G3, README.md:105-110 / util.pyx:39 of the reference).
+// (w & 0x06060606) holds 2*code per byte; the multiply gathers the four 2-bit fields
+// into bits 24..31 with no carries between partial products.
+__device__ __forceinline__ u32 gather4(u32 w) { return (w & 0x06060606u) * 0x00820820u; }
+
+// Exact {A,C,G,T} test of four bytes at once: returns a word that is non-zero iff
+// some byte is not one of 0x41 0x43 0x47 0x54.  With m = [code == 2] (bit2 & ~bit1) per
+// byte, a valid byte equals 0x41 | (code<<1) with 0x11 flipped when m: A,C,G keep
+// bits 4,0 = 0,1 and T has them 1,0.
+__device__ __forceinline__ u32 invalid4(u32 w) {
+    u32 s1 = w >> 1;
+    u32 m = (s1 >> 1) & ~s1 & 0x01010101u;
+    u32 x = (w & 0xF9F9F9F9u) ^ (m * 0x11u);
+    return x ^ 0x41414141u;
+}
+
+// 16 ASCII bytes (one uint4) -> 32 bits of codes (base k in bits 2k..2k+1); `bad`
+// accumulates the invalid-byte indicator.
+__device__ __forceinline__ u32 encode16(uint4 v, u32 &bad) {
+    bad |= invalid4(v.x) | invalid4(v.y) | invalid4(v.z) | invalid4(v.w);
+    u32 a = gather4(v.x), b = gather4(v.y), c = gather4(v.z), d = gather4(v.w);
+    // pick the top byte of each: result = a.b3 | b.b3<<8 | c.b3<<16 | d.b3<<24
+    u32 ab = __byte_perm(a, b, 0x0073);   // byte0 = a.b3, byte1 = b.b3
+    u32 cd = __byte_perm(c, d, 0x0073);
+    return __byte_perm(ab, cd, 0x5410);
+}
+
+// Exact per-byte test used on the rare slow path and for error positions.
+__host__ __device__ __forceinline__ bool is_acgt(uint8_t c) {
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+// popcount(((x>>1)|x) & 0x5555...) -- number of differing bases of one block
+// (short_seq_64.pyx:82-84 of the reference).
+__device__ __forceinline__ int diff_bases(u64 a, u64 b) {
+    u64 x = a ^ b;
+    x = ((x >> 1) | x) & 0x5555555555555555ull;
+    return __popcll(x);
+}
+
+}  // namespace ssq

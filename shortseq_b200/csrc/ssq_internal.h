@@ -1,0 +1,74 @@
+// ssq_internal.h -- host-side structures behind the opaque C-ABI handles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/shortseq_b200.h"
+#include "ssq_device.cuh"
+
+struct ssq_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;          // the stream work is enqueued on (own or external)
+    cudaStream_t copy_streams[2]; // host pipeline: H2D / D2H
+    ssq::DevReport *d_report;     // device error record
+    ssq::DevReport *h_report;     // pinned mirror
+};
+
+struct ssq_counter {
+    ssq_ctx *ctx;
+    int klass;            // SSQ_CLASS_64 | SSQ_CLASS_192
+    int hash_rot;
+    int log2_cap;         // capacity = 1 << log2_cap slots
+    void *slots;          // class 64: {key, count}[cap] (16 B); class 192: {meta, w0, w1, w2}[cap] (32 B)
+    ssq::u64 *first_idx;  // optional side array [cap] (lazily allocated)
+    ssq::u64 *d_size;     // number of occupied slots (device)
+    ssq::u64 *h_size;     // pinned
+    ssq::u64 *d_gate;     // {stop flag, first stopped sub-batch} (device, see run_gated)
+    ssq::u64 *h_gate;     // pinned
+};
+
+namespace ssq {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SSQ_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return ssq::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SSQ_LAUNCH_CHECK() SSQ_CUDA(cudaGetLastError())
+
+#define SSQ_ARG(cond, msg)                                   \
+    do {                                                     \
+        if (!(cond)) { ssq::set_error("invalid argument: %s", msg); return SSQ_ERR_ARG; } \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// grid size for a grid-stride kernel: enough CTAs to fill the GPU, capped by the work
+inline int grid_for(const ssq_ctx *ctx, int64_t work_items, int ctas_per_sm) {
+    int64_t g = (int64_t)ctx->sm_count * ctas_per_sm;
+    if (work_items < g) g = work_items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// fused pack+count over a (possibly staged) slice (ssq_counter.cu)
+int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets, int64_t n,
+                    int64_t index_base, u64 *words, uint8_t *lens);
+
+// exclusive scan helpers (ssq_scan.cu)
+int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out);
+int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off);
+int scan_synth_lens(ssq_ctx *ctx, uint64_t seed, int64_t first_read, int64_t n, int64_t n_keys,
+                    int32_t len_lo, int32_t len_hi, int64_t *offsets);
+
+}  // namespace ssq

@@ -1,0 +1,129 @@
+"""GPU: the reference's per-object Python API (sq.pack, ShortSeq*, ShortSeqCounter) as a drop-in.
+
+Mirrors shortseq/tests/unit_tests_main.py of the reference.
+"""
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_seq(rng, n):
+    return "".join(rng.choice("ACGT") for _ in range(n))
+
+
+def test_empty_seq(sq):
+    a, b = sq.pack(""), sq.pack(b"")
+    assert a is b and str(a) == "" and len(a) == 0 and a == ""
+    assert isinstance(a, sq.ShortSeq64)
+
+
+def test_single_bases_and_types(sq):
+    for c in "ACGT":
+        s = sq.pack(c)
+        assert isinstance(s, sq.ShortSeq64) and s == c and str(s) == c and len(s) == 1
+        assert sq.pack(c.encode()) == c
+    assert isinstance(sq.pack("A" * 32), sq.ShortSeq64)
+    assert isinstance(sq.pack("A" * 33), sq.ShortSeq192)
+    assert isinstance(sq.pack("A" * 96), sq.ShortSeq192)
+    assert isinstance(sq.pack("A" * 97), sq.ShortSeqVar)
+    assert isinstance(sq.pack("A" * 1024), sq.ShortSeqVar)
+    with pytest.raises(TypeError, match="Cannot pack objects of type"):
+        sq.pack(12)
+    s = sq.pack("ACGT")
+    assert sq.pack(s) is s
+
+
+def test_kats_hash_eq_repr(sq):
+    assert hash(sq.pack("ACGT")) == 180 and hash(sq.pack("ATGC")) == 120 and hash(sq.pack("GATTACA")) == 1187
+    assert hash(sq.pack("G" * 32)) == -2
+    assert hash(sq.pack("ACGT" * 8)) == -5425512962855750476
+    assert hash(sq.pack("TATTAGCGATTGACAGTTGTCCTGTAATAACGCCGGGTAAATTTGCCG")) == -3421920176517882718
+    assert hash(sq.pack("A")) == hash(sq.pack("AA")) == 0 and sq.pack("A") != sq.pack("AA")
+    assert repr(sq.pack("ACGT")) == "<ShortSeq64 (4 nt): ACGT>"
+    v = sq.pack("ACGT" * 30)
+    assert repr(v) == f"<ShortSeqVar (120 nt): {('ACGT' * 30)[:75]} ... >"
+    assert v.__sizeof__() == 32 + 8 * 4
+    assert sq.pack("ACGT") != b"ACGT"      # reference quirk T6
+    assert (sq.pack("ACGT") == 5) is False
+
+
+def test_hamming_operator(sq):
+    a = sq.pack("TATTAGCGATTGACAGTTGTCCTGTAATAACGCCGGGTAAATTTGCCG")
+    b = sq.pack("TATTACCGATTGACAGTTGTCCTGTAATAACGGCGGGTAAATTTGCTG")
+    assert a ^ b == 3
+    assert sq.pack("A") ^ sq.pack("C") == 1 and sq.pack("A") ^ sq.pack("G") == 1 and sq.pack("ACGT") ^ sq.pack("ACGA") == 1
+    with pytest.raises(Exception, match="equal length"):
+        sq.pack("ACG") ^ sq.pack("ACGT")
+    with pytest.raises(TypeError):
+        sq.pack("ACG") ^ sq.pack("A" * 40)
+    rng = random.Random(3)
+    for L in (12, 31, 32, 33, 64, 95, 96, 97, 500, 1024):
+        x, y = rand_seq(rng, L), rand_seq(rng, L)
+        assert sq.pack(x) ^ sq.pack(y) == sum(p != q for p, q in zip(x, y))
+
+
+def test_subscript_and_slices(sq):
+    rng = random.Random(4)
+    for L in (5, 32, 33, 70, 96, 97, 300):
+        s = rand_seq(rng, L)
+        p = sq.pack(s)
+        for i in (0, 1, L // 2, L - 1, -1, -L):
+            assert p[i] == s[i] and isinstance(p[i], sq.ShortSeq64)
+        with pytest.raises(IndexError):
+            p[L]
+        with pytest.raises(IndexError):
+            p[-L - 1]
+        with pytest.raises(TypeError, match="Slice step not supported"):
+            p[::2]
+        with pytest.raises(TypeError, match="Invalid index type"):
+            p["a"]
+        assert p[3:3] is sq.empty
+        for _ in range(40):
+            a = rng.randrange(0, L); b = rng.randrange(a, L + 1)
+            sl = p[a:b]
+            assert str(sl) == s[a:b] and len(sl) == b - a
+            n = b - a
+            want = sq.ShortSeq64 if n <= 32 else sq.ShortSeq192 if n <= 96 else sq.ShortSeqVar
+            assert isinstance(sl, want)
+            if n:
+                assert sl == sq.pack(s[a:b]) and hash(sl) == hash(sq.pack(s[a:b]))
+    # Hamming after slicing needs trimmed tails (reference unit_tests_main.py:402-435)
+    x, y = sq.pack("ACGT" * 10), sq.pack("ACGA" * 10)
+    assert x[2:30] ^ y[2:30] == 7
+    assert list(zip(sq.pack("ACG"), "ACG")) == [(sq.pack("A"), "A"), (sq.pack("C"), "C"), (sq.pack("G"), "G")]
+
+
+def test_counter_readme_and_kats(sq):
+    c = sq.ShortSeqCounter([b"ATGC"] * 10)
+    assert c == {sq.pack("ATGC"): 10}
+    c = sq.ShortSeqCounter([b"ACGT", b"TTTT", b"ACGT", b"GG", b"TTTT", b"ACGT"])
+    assert [(str(k), v) for k, v in c.items()] == [("ACGT", 3), ("TTTT", 2), ("GG", 1)]
+    c = sq.ShortSeqCounter([b"A", b"AA", b"AAA", b"A"])
+    assert [(str(k), v) for k, v in c.items()] == [("A", 2), ("AA", 1), ("AAA", 1)]
+    c = sq.ShortSeqCounter([b"", b"", b"A"])
+    assert [(str(k), v) for k, v in c.items()] == [("", 2), ("A", 1)]
+    assert sq.ShortSeqCounter((b"ACGT",)) == {}            # only lists are consumed (counter.pyx:14)
+    with pytest.raises(TypeError, match="expected bytes, str found"):
+        sq.ShortSeqCounter(["ACGT"])
+    with pytest.raises(TypeError, match="does not support"):
+        sq.ShortSeqCounter()["ACGT"] = 1
+    with pytest.raises(Exception, match="Unsupported base character: N"):
+        sq.ShortSeqCounter([b"ACGT", b"ACNT", b"AC*T"])
+    # mixed 64 / 192 classes keep global first-occurrence order
+    long = b"ACGT" * 12
+    c = sq.ShortSeqCounter([long, b"ACGT", long, b"GG", b"ACGT"])
+    assert [(str(k), v) for k, v in c.items()] == [(long.decode(), 2), ("ACGT", 2), ("GG", 1)]
+
+
+def test_counter_from_batch_matches_collections_counter(sq):
+    import collections
+    rng = random.Random(9)
+    pool = [rand_seq(rng, rng.randrange(15, 31)).encode() for _ in range(500)]
+    reads = [rng.choice(pool) for _ in range(20_000)]
+    c = sq.ShortSeqCounter(reads)
+    ref = collections.Counter(reads)
+    assert len(c) == len(ref)
+    assert [str(k).encode() for k in c] == list(ref)            # same first-occurrence order
+    assert all(c[sq.pack(k)] == v for k, v in list(ref.items())[:50])

@@ -1,0 +1,327 @@
+"""GPU parity: every CUDA path through the C ABI against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import concat, counter_dict, rand_reads
+
+pytestmark = pytest.mark.gpu
+
+CLASS_RANGE = {0: (0, 32), 1: (33, 96), 2: (97, 1024)}
+
+
+def _pack_and_compare(sq, oracle, reads, klass):
+    buf, off = concat(reads)
+    arr = sq.pack_batch(buf, off, klass=klass)
+    w, l, wo = arr.to_host()
+    ow, ol, owo = oracle.pack_batch(klass, buf, off)
+    assert np.array_equal(l.astype(np.int64), ol.astype(np.int64))
+    assert np.array_equal(w, ow)
+    if klass == 2:
+        assert np.array_equal(wo, owo)
+    return arr
+
+
+@pytest.mark.parametrize("klass", [0, 1, 2])
+def test_pack_every_length(sq, oracle, klass):
+    """reference tests: test_length_range / test_min_length / test_max_length (unit_tests_main.py:91-118,249-287)."""
+    rng = np.random.default_rng(10 + klass)
+    lo, hi = CLASS_RANGE[klass]
+    reads = []
+    for L in range(lo, hi + 1):
+        reads += rand_reads(rng, 2 if klass == 2 else 5, L, L)
+    rng.shuffle(reads)
+    _pack_and_compare(sq, oracle, reads, klass)
+
+
+@pytest.mark.parametrize("klass,n", [(0, 100_000), (1, 50_000), (2, 3_000)])
+def test_pack_random_batches(sq, oracle, klass, n):
+    rng = np.random.default_rng(20 + klass)
+    lo, hi = CLASS_RANGE[klass]
+    _pack_and_compare(sq, oracle, rand_reads(rng, n, lo, hi), klass)
+
+
+@pytest.mark.parametrize("klass,L", [(0, 32), (0, 22), (0, 1), (1, 75), (1, 96), (2, 150), (2, 1024)])
+def test_pack_fixed_length(sq, oracle, klass, L):
+    rng = np.random.default_rng(30 + L)
+    _pack_and_compare(sq, oracle, rand_reads(rng, 4099, L, L), klass)
+
+
+def test_pack_homopolymers_and_kats(sq, oracle):
+    reads = [b"A" * 32, b"C" * 32, b"G" * 32, b"T" * 32, b"ACGT", b"ATGC", b"GATTACA", b"TGACTGACTGAC",
+             b"TGAGGTAGTAGGTTGTATAGTT", b"ACGT" * 8, b"", b"A", b"AA"]
+    arr = _pack_and_compare(sq, oracle, reads, 0)
+    w, _, _ = arr.to_host()
+    assert [int(x) for x in w[4:9]] == [0xb4, 0x78, 0x4a3, 0x4e4e4e, 0xac8baf2cbce]
+    assert int(w[2]) == 0xFFFFFFFFFFFFFFFF and int(w[9]) == 0xb4b4b4b4b4b4b4b4
+    arr = _pack_and_compare(sq, oracle, [b"GCGTAATAGGGGGTTTCGCTGTGGGGCGGCTAG", b"A" * 32 + b"C", b"ACGT" * 24], 1)
+    w, _, _ = arr.to_host()
+    assert [int(x) for x in w[0]] == [0x27dffb9dabff20b7, 0x3, 0x0]
+    assert [int(x) for x in w[1]] == [0, 1, 0]
+    _pack_and_compare(sq, oracle, [b"ACGT" * 24 + b"T"], 2)
+
+
+def test_pack_empty_batch(sq):
+    arr = sq.pack_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64), klass=0)
+    assert len(arr) == 0
+
+
+def test_pack_unaligned_device_buffer(sq, oracle):
+    """The ASCII pointer handed to the C ABI need not be 16-byte aligned."""
+    rng = np.random.default_rng(5)
+    reads = rand_reads(rng, 3000, 0, 32)
+    buf, off = concat(reads)
+    for shift in (1, 3, 8, 15):
+        dev = torch.zeros(len(buf) + 32, dtype=torch.uint8, device="cuda")
+        dev[shift:shift + len(buf)] = torch.from_numpy(buf).cuda()
+        arr = sq.pack_batch(dev[shift:shift + len(buf)], torch.from_numpy(off).cuda(), klass=0)
+        ow, ol, _ = oracle.pack_batch(0, buf, off)
+        w, l, _ = arr.to_host()
+        assert np.array_equal(w, ow) and np.array_equal(l, ol)
+
+
+def test_every_byte_value_validation(sq):
+    """Exact {A,C,G,T} validation for all 256 byte values (the reference's bloom lets 16 aliases through)."""
+    for c in range(256):
+        for L, klass in ((1, 0), (20, 0), (40, 1), (130, 2)):
+            read = bytearray(b"ACGT" * 40)[:L]
+            read[L // 2] = c
+            ok = bytes([c]) in (b"A", b"C", b"G", b"T")
+            if ok:
+                sq.pack_batch([bytes(read)], klass=klass)
+            else:
+                with pytest.raises(Exception, match="Unsupported base character"):
+                    sq.pack_batch([bytes(read)], klass=klass)
+
+
+def test_bad_base_reports_lowest_read_and_reference_message(sq, oracle):
+    """reference: test_incompatible_seq_chars (unit_tests_main.py:63-69,504-515) + SURVEY KAT-20."""
+    rng = np.random.default_rng(7)
+    reads = rand_reads(rng, 5000, 10, 32)
+    for bad_at in (4999, 2500, 17):
+        r = bytearray(reads[bad_at]); r[len(r) // 2] = ord("N"); reads[bad_at] = bytes(r)
+        with pytest.raises(Exception, match="Unsupported base character: N"):
+            sq.pack_batch(reads, klass=0)
+        from shortseq_b200 import _lib
+        from shortseq_b200.batch import ReadBatch, _pack_raw
+        _, rep = _pack_raw(ReadBatch.make(reads), 0)
+        assert rep.code == _lib.ERR_BAD_BASE and rep.first_bad_read == bad_at
+    # message forms of the reference
+    for read, msg in [(b"N", "N"), (b"*", r"\*"), (b"U", "U"), (b"a", "a"), (b"acgt", "t"),
+                      (b"A" * 32 + b"N", "N"), (b"A" * 8 + b"N" + b"A" * 25, "NAAAAAAA")]:
+        with pytest.raises(Exception, match="Unsupported base character: " + msg):
+            sq.pack(read)
+        with pytest.raises(oracle.OracleError):
+            oracle.pack_one(read)
+
+
+def test_last_char_bad_every_var_length(sq):
+    """reference unit_tests_main.py:504-515: last char bad for every L in 97..1023."""
+    reads = [b"A" * (L - 1) + b"N" for L in range(97, 1024)]
+    from shortseq_b200 import _lib
+    from shortseq_b200.batch import ReadBatch, _pack_raw
+    for i in (0, 500, len(reads) - 1):
+        good = [b"A" * len(r) for r in reads]
+        good[i] = reads[i]
+        _, rep = _pack_raw(ReadBatch.make(good), 2)
+        assert rep.code == _lib.ERR_BAD_BASE and rep.first_bad_read == i
+
+
+def test_length_errors(sq):
+    with pytest.raises(Exception, match="longer than 1024 bases"):
+        sq.pack(b"A" * 1025)
+    with pytest.raises(sq.ShortSeqClassError):
+        sq.pack_batch([b"A" * 10, b"A" * 40], klass=0)
+    with pytest.raises(sq.ShortSeqClassError):
+        sq.pack_batch([b"A" * 40, b"A" * 10], klass=1)
+    with pytest.raises(Exception, match="longer than 1024 bases"):
+        sq.pack_batch([b"A" * 100, b"A" * 2000], klass=2)
+
+
+@pytest.mark.parametrize("klass,n", [(0, 50_000), (1, 20_000), (2, 2_000)])
+def test_decode_round_trip(sq, oracle, klass, n):
+    """reference: test_length_range round trips (str(pack(s)) == s)."""
+    rng = np.random.default_rng(40 + klass)
+    lo, hi = CLASS_RANGE[klass]
+    reads = rand_reads(rng, n, lo, hi)
+    buf, off = concat(reads)
+    arr = sq.pack_batch(buf, off, klass=klass)
+    out, out_off = arr.decode()
+    assert np.array_equal(out_off.cpu().numpy(), off)
+    assert np.array_equal(out.cpu().numpy(), buf)
+    w, l, wo = arr.to_host()
+    oa, _ = oracle.decode_batch(w, l, stride=3 if klass == 1 else 1, word_off=wo)
+    assert np.array_equal(oa, buf)
+
+
+@pytest.mark.parametrize("klass,n", [(0, 50_000), (1, 20_000), (2, 2_000)])
+def test_hamming_pairs(sq, oracle, klass, n):
+    """reference: test_hamming_distance (unit_tests_main.py:159-166,456-463)."""
+    rng = np.random.default_rng(50 + klass)
+    lo, hi = CLASS_RANGE[klass]
+    a = rand_reads(rng, n, lo, hi)
+    b = []
+    for r in a:  # mutate a few positions
+        m = bytearray(r)
+        for _ in range(rng.integers(0, 6)):
+            if m:
+                m[rng.integers(0, len(m))] = b"ACGT"[rng.integers(0, 4)]
+        b.append(bytes(m))
+    A, B = sq.pack_batch(a, klass=klass), sq.pack_batch(b, klass=klass)
+    d = sq.hamming_batch(A, B).cpu().numpy().astype(np.int64)
+    expect = np.array([sum(x != y for x, y in zip(ra, rb)) for ra, rb in zip(a, b)])
+    assert np.array_equal(d, expect)
+    if klass != 2:
+        aw, al, _ = A.to_host(); bw, bl, _ = B.to_host()
+        od = oracle.hamming_batch(aw, bw, al, bl, 3 if klass == 1 else 1)
+        assert np.array_equal(d, od)
+
+
+def test_hamming_length_mismatch(sq):
+    A, B = sq.pack_batch([b"ACGT", b"ACG"], klass=0), sq.pack_batch([b"ACGT", b"ACGT"], klass=0)
+    with pytest.raises(Exception, match="equal length"):
+        sq.hamming_batch(A, B)
+
+
+def test_hamming_refset(sq):
+    rng = np.random.default_rng(60)
+    for klass, L in ((0, 12), (1, 96)):
+        refs = rand_reads(rng, 1500, L, L) + rand_reads(rng, 10, L - 1, L - 1)
+        q = rand_reads(rng, 3000, L, L)
+        Q, R = sq.pack_batch(q, klass=klass), sq.pack_batch(refs, klass=klass)
+        md, am, within = sq.hamming_refset(Q, R, thresh=L // 2)
+        qa = np.array([list(x) for x in q], dtype=np.uint8)
+        ra = np.array([list(x) for x in refs[:1500]], dtype=np.uint8)
+        dist = (qa[:, None, :] != ra[None, :, :]).sum(-1)
+        assert np.array_equal(md.cpu().numpy(), dist.min(1))
+        assert np.array_equal(am.cpu().numpy(), dist.argmin(1))
+        assert np.array_equal(within.cpu().numpy(), (dist <= L // 2).sum(1))
+
+
+@pytest.mark.parametrize("klass,n,u,lo,hi", [(0, 200_000, 5_000, 15, 32), (0, 100_000, 100_000, 32, 32),
+                                            (0, 50_000, 40, 0, 3), (1, 100_000, 3_000, 33, 96),
+                                            (1, 50_000, 50_000, 75, 75)])
+def test_counter_vs_oracle(sq, oracle, klass, n, u, lo, hi):
+    """reference: ShortSeqCounter (counter.pyx:41-54); key = (length, words)."""
+    rng = np.random.default_rng(70 + klass + u)
+    pool = rand_reads(rng, u, lo, hi)
+    reads = [pool[i] for i in rng.integers(0, u, size=n)]
+    buf, off = concat(reads)
+    ctr = sq.DeviceCounter(klass, expected_unique=0)           # starts at the minimum size: exercises growth
+    arr = ctr.pack_count(buf, off)
+    ctr.track_first_index(arr)
+    keys, counts, first, parts = ctr.export(1, with_first_index=True)
+    kw, kl, _ = keys.to_host()
+    ow, ol, _ = oracle.pack_batch(klass, buf, off)
+    uw, ul, uc, ufi = oracle.count(ow, ol, 3 if klass == 1 else 1)
+    assert len(ctr) == len(ul) == int(parts.sum())
+    got = counter_dict(kw, kl, counts.cpu().numpy())
+    exp = counter_dict(uw, ul, uc)
+    assert got == exp
+    gfirst = counter_dict(kw, kl, first.cpu().numpy())
+    efirst = counter_dict(uw, ul, ufi)
+    assert gfirst == efirst
+    # lookup
+    probe = sq.pack_batch(buf, off, klass=klass)
+    c = ctr.lookup(probe).cpu().numpy()
+    assert all(c[i] == exp[(int(ol[i]), (int(ow[i]),) if klass == 0 else tuple(int(x) for x in ow[i]))] for i in range(0, n, 997))
+
+
+def test_counter_incremental_and_insert_packed(sq, oracle):
+    rng = np.random.default_rng(81)
+    pool = rand_reads(rng, 2000, 18, 30)
+    ctr = sq.DeviceCounter(0, expected_unique=100)
+    all_reads = []
+    for step in range(4):
+        reads = [pool[i] for i in rng.integers(0, 2000, size=30_000)]
+        all_reads += reads
+        if step % 2:
+            ctr.insert(sq.pack_batch(reads, klass=0))
+        else:
+            ctr.pack_count(reads)
+    buf, off = concat(all_reads)
+    ow, ol, _ = oracle.pack_batch(0, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 1)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == counter_dict(uw, ul, uc)
+
+
+@pytest.mark.parametrize("klass", [0, 1])
+def test_counter_export_partitions_and_merge(sq, oracle, klass):
+    """Hash-partitioned export + weighted merge = the single-GPU form of the multi-GPU all-to-all."""
+    rng = np.random.default_rng(90 + klass)
+    lo, hi = (20, 32) if klass == 0 else (40, 90)
+    pool = rand_reads(rng, 20_000, lo, hi)
+    shards = [[pool[i] for i in rng.integers(0, 20_000, size=60_000)] for _ in range(4)]
+    P = 4
+    owners = [sq.DeviceCounter(klass, expected_unique=8000, hash_rot=2) for _ in range(P)]
+    for shard in shards:
+        local = sq.DeviceCounter(klass, expected_unique=30_000)
+        local.pack_count(shard)
+        keys, counts, _, parts = local.export(P)
+        parts = parts.cpu().numpy()
+        assert parts.sum() == len(local)
+        start = 0
+        for p in range(P):
+            sl = slice(start, start + int(parts[p]))
+            owners[p].merge(keys.words[sl].contiguous(), keys.lens[sl].contiguous(), counts[sl].contiguous())
+            start += int(parts[p])
+    merged = {}
+    for o in owners:
+        keys, counts, _, _ = o.export(1)
+        kw, kl, _ = keys.to_host()
+        d = counter_dict(kw, kl, counts.cpu().numpy())
+        assert not (set(d) & set(merged)), "a key landed on two owners"
+        merged.update(d)
+    buf, off = concat([r for s in shards for r in s])
+    ow, ol, _ = oracle.pack_batch(klass, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 3 if klass == 1 else 1)
+    assert merged == counter_dict(uw, ul, uc)
+
+
+def test_counter_skewed_hot_keys(sq, oracle):
+    """A few keys carry most of the reads (small-RNA like): contended atomics must stay exact."""
+    rng = np.random.default_rng(99)
+    pool = rand_reads(rng, 1000, 20, 24)
+    idx = np.minimum((rng.pareto(0.7, size=300_000)).astype(np.int64), 999)
+    reads = [pool[i] for i in idx]
+    ctr = sq.DeviceCounter(0, expected_unique=2000)
+    ctr.pack_count(reads)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    buf, off = concat(reads)
+    ow, ol, _ = oracle.pack_batch(0, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 1)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == counter_dict(uw, ul, uc)
+
+
+def test_synth_reads_match_oracle(sq, oracle):
+    for lo, hi, n, u in ((32, 32, 10_000, 300), (22, 22, 5000, 100), (33, 96, 4000, 500), (97, 1024, 300, 50)):
+        b = sq.synth_reads(n, u, lo, hi, seed=0x5EED0001, first_read=123)
+        oa, oo = oracle.synth_reads(0x5EED0001, 123, n, u, lo, hi)
+        assert np.array_equal(b.offsets.cpu().numpy(), oo)
+        assert np.array_equal(b.ascii.cpu().numpy(), oa)
+
+
+def test_host_pipeline(sq, oracle):
+    """ssq_host_pack_count: host buffers in, packed words + counts out, chunked."""
+    import ctypes as C
+    from shortseq_b200 import _lib
+    rng = np.random.default_rng(111)
+    pool = rand_reads(rng, 3000, 10, 32)
+    reads = [pool[i] for i in rng.integers(0, 3000, size=100_000)]
+    buf, off = concat(reads)
+    ctr = sq.DeviceCounter(0, expected_unique=4000)
+    words = np.zeros(len(reads), np.uint64)
+    lens = np.zeros(len(reads), np.uint8)
+    rep = _lib.Report()
+    _lib.check(_lib.lib().ssq_host_pack_count(ctr.ctx.bind(), ctr.handle, buf.ctypes.data, off.ctypes.data, len(reads),
+                                             words.ctypes.data, lens.ctypes.data, 7777, C.byref(rep)))
+    assert rep.code == 0
+    ow, ol, _ = oracle.pack_batch(0, buf, off)
+    assert np.array_equal(words, ow) and np.array_equal(lens, ol)
+    uw, ul, uc, _ = oracle.count(ow, ol, 1)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == counter_dict(uw, ul, uc)
