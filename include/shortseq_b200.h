@@ -72,11 +72,15 @@ typedef struct ssq_report {
 /* ---- library / context ------------------------------------------------- */
 int ssq_abi_version(void);
 const char *ssq_last_error(void);      /* thread-local message for the last SSQ_ERR_CUDA / SSQ_ERR_ARG */
+uint64_t ssq_launch_count(void);      /* kernels this library has launched in this process (all contexts) */
 int ssq_device_count(int *count);
 int ssq_ctx_create(int device, ssq_ctx **out);
 int ssq_ctx_destroy(ssq_ctx *ctx);
-/* Use an externally owned cudaStream_t (e.g. the caller framework's current stream); NULL restores the context's own. */
+/* Enqueue on an externally owned cudaStream_t (e.g. the caller framework's current stream).  The handle
+ * is used as given: NULL is CUDA's legacy default stream.  ssq_ctx_reset_stream() returns to the
+ * context's own (non-blocking) stream, which is what a new context uses. */
 int ssq_ctx_set_stream(ssq_ctx *ctx, void *cuda_stream);
+int ssq_ctx_reset_stream(ssq_ctx *ctx);
 void *ssq_ctx_stream(ssq_ctx *ctx);
 /* Wait for all enqueued work, fetch and clear the device error record. */
 int ssq_ctx_sync(ssq_ctx *ctx, ssq_report *report);

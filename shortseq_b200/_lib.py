@@ -27,10 +27,12 @@ _p, _i64, _i32, _int, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_uint
 PROTOTYPES = {
     "ssq_abi_version": (_int, []),
     "ssq_last_error": (C.c_char_p, []),
+    "ssq_launch_count": (_u64, []),
     "ssq_device_count": (_int, [C.POINTER(_int)]),
     "ssq_ctx_create": (_int, [_int, C.POINTER(_p)]),
     "ssq_ctx_destroy": (_int, [_p]),
     "ssq_ctx_set_stream": (_int, [_p, _p]),
+    "ssq_ctx_reset_stream": (_int, [_p]),
     "ssq_ctx_stream": (_p, [_p]),
     "ssq_ctx_sync": (_int, [_p, C.POINTER(Report)]),
     "ssq_malloc": (_int, [_p, C.c_size_t, C.POINTER(_p)]),

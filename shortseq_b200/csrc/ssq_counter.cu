@@ -494,6 +494,7 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
         export_scatter_kernel<SSQ_CLASS_192><<<grid2, kThreads, 0, st>>>(t, log2_parts, cursors, (u64 *)words, lens,
                                                                          (u64 *)counts, first_idx);
     }
+    count_launch(); count_launch(); count_launch();
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(cursors, st);
     if (e != cudaSuccess) return cuda_fail(e, "export kernels", __FILE__, __LINE__);

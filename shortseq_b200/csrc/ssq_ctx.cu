@@ -1,5 +1,7 @@
 // ssq_ctx.cu -- contexts, error plumbing and memory helpers of the C ABI.
+#include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "ssq_internal.h"
 
@@ -20,6 +22,15 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return SSQ_ERR_CUDA;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool debug_sync() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SSQ_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 __global__ void reset_report_kernel(DevReport *r) {
     r->first_bad_base = kNoIndex;
     r->first_bad_len = kNoIndex;
@@ -37,6 +48,8 @@ extern "C" {
 int ssq_abi_version(void) { return SSQ_ABI_VERSION; }
 
 const char *ssq_last_error(void) { return g_err; }
+
+uint64_t ssq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int ssq_device_count(int *count) {
     SSQ_ARG(count != nullptr, "count is NULL");
@@ -89,7 +102,13 @@ int ssq_ctx_destroy(ssq_ctx *ctx) {
 
 int ssq_ctx_set_stream(ssq_ctx *ctx, void *cuda_stream) {
     SSQ_ARG(ctx != nullptr, "ctx is NULL");
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return SSQ_OK;
+}
+
+int ssq_ctx_reset_stream(ssq_ctx *ctx) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    ctx->stream = ctx->own_stream;
     return SSQ_OK;
 }
 

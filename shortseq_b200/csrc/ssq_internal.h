@@ -40,7 +40,16 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (e__ != cudaSuccess) return ssq::cuda_fail(e__, #call, __FILE__, __LINE__); \
     } while (0)
 
-#define SSQ_LAUNCH_CHECK() SSQ_CUDA(cudaGetLastError())
+// SSQ_DEBUG_SYNC=1 in the environment makes every launch synchronous so that a device fault is
+// attributed to the kernel that caused it (compute-sanitizer is not available on the GPU pool).
+bool debug_sync();
+void count_launch();   // every kernel launch of this library is counted (ssq_launch_count)
+#define SSQ_LAUNCH_CHECK()                                        \
+    do {                                                          \
+        ssq::count_launch();                                      \
+        SSQ_CUDA(cudaGetLastError());                             \
+        if (ssq::debug_sync()) SSQ_CUDA(cudaDeviceSynchronize()); \
+    } while (0)
 
 #define SSQ_ARG(cond, msg)                                   \
     do {                                                     \

@@ -1,0 +1,99 @@
+"""CPU: host-side logic of the Python layer (no kernels): object protocol on boxed words, slicing,
+error-message formatting, class splitting, partition hashing.  Packed words come from the oracle."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from shortseq_b200 import hashing
+from shortseq_b200._runtime import bad_base_message, gather_reads
+from shortseq_b200.batch import class_of_length, split_by_class
+from shortseq_b200.short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box, empty
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.json")))
+TYPES = {"ShortSeq64": ShortSeq64, "ShortSeq192": ShortSeq192, "ShortSeqVar": ShortSeqVar}
+
+
+def box(seq: str):
+    k, w = O.pack_one(seq.encode())
+    return _box(k, [int(x) for x in w], len(seq))
+
+
+def test_hash_len_eq_match_reference_golden():
+    for e in GOLDEN["pack"]:
+        o = box(e["seq"])
+        assert type(o).__name__ == e["type"] and len(o) == e["len"] and hash(o) == e["hash"]
+    a, aa = box("A"), box("AA")
+    assert hash(a) == hash(aa) == 0 and a != aa and a == box("A") and not (a == 5)
+    d = {box("ACGT"): 1}
+    assert box("ACGT") in d and box("ACGA") not in d
+
+
+def test_slices_match_reference_golden():
+    for e in GOLDEN["slices"]:
+        o = box(e["seq"])
+        sl = o[e["start"]:e["stop"]]
+        if e["stop"] == e["start"]:
+            assert sl is empty
+            continue
+        assert type(sl) is TYPES[e["type"]]
+        assert [f"{w:#x}" for w in sl._packed][: len(e["words"])] == e["words"]
+        assert hash(sl) == e["hash"] and len(sl) == e["stop"] - e["start"]
+        assert sl == box(e["seq"][e["start"]:e["stop"]])
+
+
+def test_subscript_and_index_errors():
+    rng = random.Random(1)
+    for L in (1, 32, 33, 96, 97, 500):
+        s = "".join(rng.choice("ACGT") for _ in range(L))
+        o = box(s)
+        for i in (0, L - 1, -1, -L, L // 2):
+            assert o[i] == box(s[i]) and type(o[i]) is ShortSeq64
+        with pytest.raises(IndexError, match="Sequence index out of range"):
+            o[L]
+        with pytest.raises(TypeError, match="Slice step not supported"):
+            o[::2]
+        with pytest.raises(TypeError, match="Invalid index type"):
+            o[1.5]
+    with pytest.raises(TypeError):
+        ShortSeq64()
+
+
+def test_bad_base_messages_match_reference_golden():
+    for e in GOLDEN["rejects"]:
+        if "longer than" in e["message"]:
+            with pytest.raises(Exception, match="longer than 1024"):
+                class_of_length(len(e["seq"]))
+        else:
+            assert bad_base_message(e["seq"].encode()) == e["message"]
+
+
+def test_gather_and_split_by_class():
+    reads = [b"ACGT", b"A" * 40, b"", b"C" * 200, b"GG", b"T" * 96, b"A" * 97]
+    buf, off = gather_reads(reads)
+    assert buf.tobytes() == b"".join(reads) and list(np.diff(off)) == [len(r) for r in reads]
+    parts = {k: (idx, a, o) for k, idx, a, o in split_by_class(buf, off)}
+    assert list(parts[0][0]) == [0, 2, 4] and list(parts[1][0]) == [1, 5] and list(parts[2][0]) == [3, 6]
+    for k, (idx, a, o) in parts.items():
+        assert [a[o[j]:o[j + 1]].tobytes() for j in range(len(idx))] == [reads[i] for i in idx]
+    with pytest.raises(TypeError, match="expected bytes, str found"):
+        gather_reads([b"A", "C"])
+
+
+def test_owner_rank_partitions_evenly_and_by_full_key():
+    rng = np.random.default_rng(0)
+    w = rng.integers(0, 2**63, size=20000, dtype=np.int64).astype(np.uint64)
+    l = np.full(20000, 32)
+    for world in (1, 2, 4, 8):
+        r = hashing.owner_rank(w, l, 0, world)
+        assert r.min() >= 0 and r.max() < world
+        assert np.bincount(r, minlength=world).min() > 20000 / world * 0.9
+    w3 = np.stack([w, w[::-1], w ^ np.uint64(5)], axis=1)
+    r1 = hashing.owner_rank(w3, np.full(20000, 75), 1, 8)
+    r2 = hashing.owner_rank(w3, np.full(20000, 76), 1, 8)
+    assert (r1 != r2).mean() > 0.5            # length is part of the key
+    assert int(hashing.mix64(np.uint64(0))) == int(O.lib().ssq_oracle_mix64(0))
+    assert int(hashing.mix64(np.uint64(12345))) == int(O.lib().ssq_oracle_mix64(12345))
