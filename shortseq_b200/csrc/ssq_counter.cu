@@ -7,15 +7,24 @@
 //     "gate" kernel that sets a stop flag when the table could exceed 75 % load during the
 //     sub-batch; kernels behind a raised flag do nothing.  The host synchronises once per
 //     batch, and only if the flag was raised grows the table (x4, rehash on the device) and
-//     resumes from the stopped sub-batch -- so a well-sized table costs no extra syncs and an
-//     undersized one is still exact.
+//     resumes from the stopped sub-batch.  This conservative mode is used when the caller gave no
+//     bound on the distinct keys (expected_unique = 0);
+//   * with a bound (expected_unique > 0, capacity >= 2x the bound) a batch is processed in ONE pass.
+//     Tables that fit in L2 take the keys directly.  Larger ShortSeq64 tables use the two-phase
+//     DEFERRED path: phase 1 (fused into the pack kernel, or scatter_packed_kernel for packed input)
+//     appends each key to one of 256 hash partitions; phase 2 (count_parts_kernel) walks the
+//     partitions in order, so all SMs insert into the same 1/256 of the table at a time and that
+//     region stays resident in L2 -- random DRAM sector traffic becomes two streaming passes over
+//     8 bytes per read.  After the pass the table grows (x2) once it is more than 60 % full; a bound
+//     exceeded so badly that probing fails is reported as SSQ_ERR_TABLE_FULL, never silently.
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
 
 namespace ssq {
 
-int launch_pack_count(ssq_ctx *ctx, int klass, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets,
-                      int64_t n, int64_t index_base, u64 *words, uint8_t *lens, const TableView &t, const u64 *stop);
+int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *ascii, int64_t lo, int64_t hi,
+                      const int64_t *offsets, int64_t n, int64_t index_base, u64 *words, uint8_t *lens,
+                      const TableView &t, const PartView &pv, const u64 *stop);
 
 constexpr int kThreads = 256;
 
@@ -121,6 +130,89 @@ __global__ void __launch_bounds__(kThreads) rehash_kernel(TableView src, TableVi
         my_new += is_new ? 1u : 0u;
     }
     block_add_new(dst, my_new, s_new);
+}
+
+// ---- deferred (hash-partitioned) inserts, ShortSeq64 ------------------------------------------
+constexpr int kScatterTile = 2048;    // keys per block and cursor bump
+
+// Phase 1 for already packed input: append every key to its hash partition.
+__global__ void __launch_bounds__(kThreads) scatter_packed_kernel(TableView t, PartView pv, const u64 *words,
+                                                                  const uint8_t *lens, int64_t n, int64_t index_base) {
+    __shared__ u32 hist[kParts];
+    __shared__ u32 pbase[kParts];
+    __shared__ u32 s_new[kThreads / 32];
+    constexpr int R = kScatterTile / kThreads;
+    u32 my_new = 0;
+    const int64_t ntiles = (n + kScatterTile - 1) / kScatterTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int p = threadIdx.x; p < kParts; p += kThreads) hist[p] = 0;
+        __syncthreads();
+        u64 key[R];
+        u32 rank[R], part[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int64_t i = tile * kScatterTile + k * kThreads + threadIdx.x;
+            key[k] = 0;
+            if (i < n) {
+                const u32 len = lens[i];
+                if (len > 32) { atomicMin(&t.rep->first_bad_len, (u64)(index_base + i)); continue; }
+                const u64 h2 = rotl64(mix64(words[i]), t.rot);
+                key[k] = key64_of(h2, len);
+                part[k] = (u32)(h2 >> 56);
+                rank[k] = atomicAdd(&hist[part[k]], 1u);
+            }
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < kParts; p += kThreads) {
+            const u32 cnt = hist[p];
+            pbase[p] = cnt ? atomicAdd(&pv.cursor[p], cnt) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (key[k] == 0) continue;
+            const u32 pos = pbase[part[k]] + rank[k];
+            if (pos < pv.cap_per_part) {
+                pv.keys[(size_t)part[k] * pv.cap_per_part + pos] = key[k];
+            } else {
+                bool is_new = false;
+                insert64_hashed(t, ((u64)part[k] << 56) | (key[k] & kMask56), key[k], 1ull, is_new);
+                my_new += is_new ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+    }
+    block_add_new(t, my_new, s_new);
+}
+
+// Phase 2: insert the partitions in order.  Block b handles keys [chunk*kScatterTile, +kScatterTile) of
+// partition b / blocks_per_part; blocks are scheduled in index order, so at any time the whole GPU
+// works on one or two neighbouring partitions whose table region (cap/256 slots) stays in L2.
+__global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, PartView pv, u32 blocks_per_part) {
+    __shared__ u32 s_new[kThreads / 32];
+    constexpr int R = kScatterTile / kThreads;
+    const u32 p = blockIdx.x / blocks_per_part;
+    const u32 chunk = blockIdx.x - p * blocks_per_part;
+    const u32 cnt = min(pv.cursor[p], pv.cap_per_part);
+    const u32 start = chunk * kScatterTile;
+    if (start >= cnt) return;
+    const u64 *keys = pv.keys + (size_t)p * pv.cap_per_part;
+    const u64 top = (u64)p << 56;
+    u64 k[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const u32 i = start + j * kThreads + threadIdx.x;
+        k[j] = i < cnt ? keys[i] : 0ull;
+    }
+    u32 my_new = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        if (k[j] == 0) continue;
+        bool is_new = false;
+        insert64_hashed(t, top | (k[j] & kMask56), k[j], 1ull, is_new);
+        my_new += is_new ? 1u : 0u;
+    }
+    block_add_new(t, my_new, s_new);
 }
 
 // ---- export ---------------------------------------------------------------------------------
@@ -308,16 +400,79 @@ static int run_gated(ssq_counter *c, int64_t n, Launch launch) {
     return SSQ_OK;
 }
 
+// Tables up to this size are assumed to stay resident in the 126 MB L2 under random inserts.
+constexpr size_t kDirectTableBytes = (size_t)48 << 20;
+
+static bool use_deferred(const ssq_counter *c, int64_t n) {
+    if (c->klass != SSQ_CLASS_64 || c->expected_unique <= 0) return false;
+    const size_t table_bytes = ((size_t)1 << c->log2_cap) * 16;
+    // worthwhile when the table cannot live in L2 and the pass brings at least ~1 key per 4 slots
+    return table_bytes > kDirectTableBytes && n >= ((int64_t)1 << c->log2_cap) / 4;
+}
+
+// Size the partition buffers for a pass of n keys and reset the cursors.
+static int prepare_parts(ssq_counter *c, int64_t n, PartView *pv) {
+    ssq_ctx *ctx = c->ctx;
+    int64_t per = n / kParts + n / (kParts * 32) + 4096;     // mean + 3 % + slack (overflow is handled, not fatal)
+    per = (per + 255) & ~(int64_t)255;
+    if (per > c->part_cap) {
+        SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (c->part_keys) SSQ_CUDA(cudaFree(c->part_keys));
+        c->part_keys = nullptr;
+        c->part_cap = 0;
+        SSQ_CUDA(cudaMalloc(&c->part_keys, sizeof(u64) * (size_t)per * kParts));
+        c->part_cap = per;
+    }
+    if (!c->part_cursor) SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * kParts));
+    SSQ_CUDA(cudaMemsetAsync(c->part_cursor, 0, sizeof(u32) * kParts, ctx->stream));
+    pv->keys = c->part_keys;
+    pv->cursor = c->part_cursor;
+    pv->cap_per_part = (u32)per;
+    return SSQ_OK;
+}
+
+static int launch_count_parts(ssq_counter *c, const PartView &pv) {
+    const u32 bpp = (pv.cap_per_part + kScatterTile - 1) / kScatterTile;
+    count_parts_kernel<<<kParts * bpp, kThreads, 0, c->ctx->stream>>>(view_of(c), pv, bpp);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+// After a single-pass (bounded) insert: wait, read the size, grow once the table is past 60 % load.
+static int finish_pass(ssq_counter *c) {
+    ssq_ctx *ctx = c->ctx;
+    SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t cap = (int64_t)1 << c->log2_cap;
+    if ((int64_t)*c->h_size > cap - cap / 4 - cap / 8 - cap / 40) return grow(c, c->log2_cap + 1);
+    return SSQ_OK;
+}
+
 // Fused pack+count of reads whose bytes are ascii[lo, hi) (ascii may be a virtual base pointer);
 // index_base is added to the read indices that data errors are reported with.
 int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets, int64_t n,
                     int64_t index_base, u64 *words, uint8_t *lens) {
     ssq_ctx *ctx = c->ctx;
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
-    return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
-        return launch_pack_count(ctx, c->klass, ascii, lo, hi, offsets + p, cnt, index_base + p, words + (size_t)p * W,
-                                 lens + p, view_of(c), stop);
-    });
+    if (c->expected_unique <= 0)
+        return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
+            return launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets + p, cnt, index_base + p,
+                                     words + (size_t)p * W, lens + p, view_of(c), PartView{}, stop);
+        });
+    int rc;
+    if (use_deferred(c, n)) {
+        PartView pv;
+        rc = prepare_parts(c, n, &pv);
+        if (rc) return rc;
+        rc = launch_pack_count(ctx, c->klass, true, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c), pv, nullptr);
+        if (rc) return rc;
+        rc = launch_count_parts(c, pv);
+    } else {
+        rc = launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c),
+                               PartView{}, nullptr);
+    }
+    if (rc) return rc;
+    return finish_pass(c);
 }
 
 }  // namespace ssq
@@ -340,6 +495,10 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->log2_cap = log2_cap_for(expected_unique);
     c->slots = nullptr;
     c->first_idx = nullptr;
+    c->expected_unique = expected_unique;
+    c->part_keys = nullptr;
+    c->part_cursor = nullptr;
+    c->part_cap = 0;
     const size_t bytes = ((size_t)1 << c->log2_cap) * slot_bytes(klass);
     SSQ_CUDA(cudaMalloc(&c->slots, bytes));
     SSQ_CUDA(cudaMalloc(&c->d_size, 4 * sizeof(u64)));
@@ -358,6 +517,8 @@ int ssq_counter_destroy(ssq_counter *c) {
     cudaStreamSynchronize(c->ctx->stream);
     cudaFree(c->slots);
     cudaFree(c->first_idx);
+    cudaFree(c->part_keys);
+    cudaFree(c->part_cursor);
     cudaFree(c->d_size);
     cudaFreeHost(c->h_size);
     delete c;
@@ -381,6 +542,29 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
+    if (c->expected_unique > 0) {
+        int rc = SSQ_OK;
+        if (counts == nullptr && use_deferred(c, n)) {
+            PartView pv;
+            rc = prepare_parts(c, n, &pv);
+            if (rc) return rc;
+            int grid = grid_for(ctx, (n + kScatterTile - 1) / kScatterTile, 6);
+            scatter_packed_kernel<<<grid, kThreads, 0, ctx->stream>>>(view_of(c), pv, (const u64 *)words, lens, n, 0);
+            SSQ_LAUNCH_CHECK();
+            rc = launch_count_parts(c, pv);
+        } else {
+            int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+            if (c->klass == SSQ_CLASS_64)
+                insert_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens,
+                                                                                (const u64 *)counts, n, 0, nullptr);
+            else
+                insert_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens,
+                                                                                 (const u64 *)counts, n, 0, nullptr);
+            SSQ_LAUNCH_CHECK();
+        }
+        if (rc) return rc;
+        return finish_pass(c);
+    }
     return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
         TableView t = view_of(c);
         int grid = grid_for(ctx, (cnt + kThreads - 1) / kThreads, 8);

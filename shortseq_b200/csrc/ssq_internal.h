@@ -27,6 +27,10 @@ struct ssq_counter {
     ssq::u64 *h_size;     // pinned
     ssq::u64 *d_gate;     // {stop flag, first stopped sub-batch} (device, see run_gated)
     ssq::u64 *h_gate;     // pinned
+    int64_t expected_unique;   // caller's bound on the distinct keys (0 = unknown: conservative gated inserts)
+    ssq::u64 *part_keys;       // partition buffers of the deferred-insert path (lazily sized)
+    ssq::u32 *part_cursor;     // [kParts]
+    int64_t part_cap;          // entries per partition currently allocated
 };
 
 namespace ssq {

@@ -26,6 +26,14 @@ namespace ssq {
 constexpr u64 kMask56 = (1ull << 56) - 1;
 constexpr int kMinLog2Cap = 16;
 
+// Hash partitions of the deferred-insert path: partition = top 8 bits of h2, i.e. 1/256 of the slot range.
+constexpr int kParts = 256;
+struct PartView {
+    u64 *keys;          // [kParts][cap_per_part] table keys (key64_of) awaiting insertion
+    u32 *cursor;        // [kParts] entries appended so far (may exceed cap_per_part: the excess was inserted directly)
+    u32 cap_per_part;
+};
+
 struct TableView {
     u64 *slots;
     u64 *first_idx;   // may be null

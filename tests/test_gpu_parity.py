@@ -325,3 +325,53 @@ def test_host_pipeline(sq, oracle):
     keys, counts, _, _ = ctr.export(1)
     kw, kl, _ = keys.to_host()
     assert counter_dict(kw, kl, counts.cpu().numpy()) == counter_dict(uw, ul, uc)
+
+
+def _oracle_counts_of_batch(oracle, b, klass):
+    buf, off = b.ascii.cpu().numpy(), b.offsets.cpu().numpy()
+    ow, ol, _ = oracle.pack_batch(klass, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 3 if klass == 1 else 1)
+    return (ow, ol), counter_dict(uw, ul, uc)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_counter_deferred_partition_path(sq, oracle, fused):
+    """Tables too large for L2 take the two-phase path (scatter to 256 hash partitions, then insert
+    partition by partition); results must be identical to the direct path and to the oracle."""
+    n, u = 3_000_000, 1_500_000
+    b = sq.synth_reads(n, u, 18, 32, seed=0x5EED0001)
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, 0)
+    ctr = sq.DeviceCounter(0, expected_unique=2_000_000)      # 2^22 slots = 64 MB > the L2-resident limit
+    assert ctr.capacity() == 1 << 22
+    if fused:
+        arr = ctr.pack_count(b)
+        w, l, _ = arr.to_host()
+        assert np.array_equal(w, ow) and np.array_equal(l, ol)
+    else:
+        ctr.insert(sq.pack_batch(b, klass=0))
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+    # a second pass over the same reads doubles every count (table already populated)
+    ctr.pack_count(b)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
+
+
+def test_counter_deferred_partition_overflow_and_growth(sq, oracle):
+    """Half of the reads are one sequence: its hash partition overflows its buffer and the excess is inserted
+    directly; the distinct keys exceed 60 % of the table, so it grows after the pass."""
+    n, u = 6_000_000, 50_000_000
+    b = sq.synth_reads(n, u, 32, 32, seed=0x5EED0009)
+    a = b.ascii.view(n, 32)
+    a[::2] = a[0].clone()                       # every second read becomes a copy of read 0
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, 0)
+    ctr = sq.DeviceCounter(0, expected_unique=2_000_000)
+    ctr.pack_count(b)
+    assert ctr.capacity() == 1 << 23            # grew
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    got = counter_dict(kw, kl, counts.cpu().numpy())
+    assert got == expect and max(got.values()) >= n // 2
