@@ -174,6 +174,10 @@ int ssq_counter_lookup(ssq_counter *c, const uint64_t *words, const uint8_t *len
 /* number of distinct keys; synchronises the context (data errors stay pending) */
 int ssq_counter_size(ssq_counter *c, int64_t *n_unique);
 int ssq_counter_capacity(ssq_counter *c, int64_t *slots);
+/* Device time (CUDA events on the context's stream) of the last single-pass ssq_counter_pack_count:
+ * phase 1 = fused pack (+ scatter to hash partitions for tables larger than L2), phase 2 = partition-ordered
+ * insertion (0 when the keys were inserted directly).  For profiling. */
+int ssq_counter_last_pass_ms(ssq_counter *c, float *phase1_ms, float *phase2_ms);
 /* Export all (key, len, count[, first_idx]) tuples, grouped into n_parts hash partitions
  * (owner = top log2(n_parts) bits of the key hash; n_parts a power of two, 1 = no
  * grouping).  Buffers must hold ssq_counter_size() tuples; part_counts[n_parts] (device)

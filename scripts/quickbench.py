@@ -54,7 +54,9 @@ def main():
     ms = timeit(pc, 3)
     nu = len(ctr)
     bytes_pc = bytes_pack + nu * (8 * W + 9)
-    print(f"pack+count:  {ms:8.3f} ms  {n*L/ms/1e6:8.1f} Gbases/s  {bytes_pc/ms/1e6:8.1f} GB/s algorithmic  uniques={nu}")
+    p1, p2 = C.c_float(), C.c_float()
+    lib.ssq_counter_last_pass_ms(ctr.handle, C.byref(p1), C.byref(p2))
+    print(f"pack+count:  {ms:8.3f} ms  {n*L/ms/1e6:8.1f} Gbases/s  {bytes_pc/ms/1e6:8.1f} GB/s algorithmic  uniques={nu}  phase1={p1.value:.3f} ms phase2={p2.value:.3f} ms")
     rep = ctx.sync()
     print("report", rep.code, rep.first_bad_read)
     arr = sq.ShortSeqArray(ctx, klass, words, lens)

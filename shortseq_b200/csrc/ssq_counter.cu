@@ -133,84 +133,83 @@ __global__ void __launch_bounds__(kThreads) rehash_kernel(TableView src, TableVi
 }
 
 // ---- deferred (hash-partitioned) inserts, ShortSeq64 ------------------------------------------
-constexpr int kScatterTile = 2048;    // keys per block and cursor bump
+constexpr int kCountKeysPerThread = 8;
 
-// Phase 1 for already packed input: append every key to its hash partition.
+// Phase 1 for already packed input: persistent CTAs stage their keys per hash partition and write whole
+// sectors to their own segments (see ssq_table.cuh).
+constexpr int kScatterRounds = 2;    // keys per thread between flushes
 __global__ void __launch_bounds__(kThreads) scatter_packed_kernel(TableView t, PartView pv, const u64 *words,
                                                                   const uint8_t *lens, int64_t n, int64_t index_base) {
-    __shared__ u32 hist[kParts];
-    __shared__ u32 pbase[kParts];
+    __shared__ __align__(16) u64 stage[kParts * kStageCap];
+    __shared__ u32 scnt[kParts];
+    __shared__ u32 sgcur[kParts];
     __shared__ u32 s_new[kThreads / 32];
-    constexpr int R = kScatterTile / kThreads;
+    static_assert(kThreads == kParts, "thread p owns partition p's staging");
+    scnt[threadIdx.x] = 0;
+    sgcur[threadIdx.x] = 0;
+    __syncthreads();
     u32 my_new = 0;
-    const int64_t ntiles = (n + kScatterTile - 1) / kScatterTile;
+    const int64_t tile_keys = (int64_t)kThreads * kScatterRounds;
+    const int64_t ntiles = (n + tile_keys - 1) / tile_keys;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int p = threadIdx.x; p < kParts; p += kThreads) hist[p] = 0;
-        __syncthreads();
-        u64 key[R];
-        u32 rank[R], part[R];
+        u64 word[kScatterRounds];
+        u32 len[kScatterRounds];
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            const int64_t i = tile * kScatterTile + k * kThreads + threadIdx.x;
-            key[k] = 0;
-            if (i < n) {
-                const u32 len = lens[i];
-                if (len > 32) { atomicMin(&t.rep->first_bad_len, (u64)(index_base + i)); continue; }
-                const u64 h2 = rotl64(mix64(words[i]), t.rot);
-                key[k] = key64_of(h2, len);
-                part[k] = (u32)(h2 >> 56);
-                rank[k] = atomicAdd(&hist[part[k]], 1u);
+        for (int k = 0; k < kScatterRounds; k++) {
+            const int64_t i = tile * tile_keys + k * kThreads + threadIdx.x;
+            len[k] = 0xFFFFFFFFu;
+            if (i < n) { word[k] = words[i]; len[k] = lens[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < kScatterRounds; k++) {
+            if (len[k] == 0xFFFFFFFFu) continue;
+            if (len[k] > 32) {
+                atomicMin(&t.rep->first_bad_len, (u64)(index_base + tile * tile_keys + k * kThreads + threadIdx.x));
+                continue;
             }
-        }
-        __syncthreads();
-        for (int p = threadIdx.x; p < kParts; p += kThreads) {
-            const u32 cnt = hist[p];
-            pbase[p] = cnt ? atomicAdd(&pv.cursor[p], cnt) : 0u;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-            if (key[k] == 0) continue;
-            const u32 pos = pbase[part[k]] + rank[k];
-            if (pos < pv.cap_per_part) {
-                pv.keys[(size_t)part[k] * pv.cap_per_part + pos] = key[k];
-            } else {
+            const u64 h2 = rotl64(mix64(word[k]), t.rot);
+            const u64 key = key64_of(h2, len[k]);
+            if (!stage_key(stage, scnt, (u32)(h2 >> 56), key)) {
                 bool is_new = false;
-                insert64_hashed(t, ((u64)part[k] << 56) | (key[k] & kMask56), key[k], 1ull, is_new);
+                insert64_hashed(t, h2, key, 1ull, is_new);
                 my_new += is_new ? 1u : 0u;
             }
         }
         __syncthreads();
+        flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, false, my_new);
+        __syncthreads();
     }
+    flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, true, my_new);
+    pv.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = sgcur[threadIdx.x];
     block_add_new(t, my_new, s_new);
 }
 
-// Phase 2: insert the partitions in order.  Block b handles keys [chunk*kScatterTile, +kScatterTile) of
-// partition b / blocks_per_part; blocks are scheduled in index order, so at any time the whole GPU
+// Phase 2: insert the partitions in order.  Block b handles the segment that scatter CTA (b % num_ctas)
+// filled for partition (b / num_ctas); blocks are scheduled in index order, so at any time the whole GPU
 // works on one or two neighbouring partitions whose table region (cap/256 slots) stays in L2.
-__global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, PartView pv, u32 blocks_per_part) {
+__global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, PartView pv) {
     __shared__ u32 s_new[kThreads / 32];
-    constexpr int R = kScatterTile / kThreads;
-    const u32 p = blockIdx.x / blocks_per_part;
-    const u32 chunk = blockIdx.x - p * blocks_per_part;
-    const u32 cnt = min(pv.cursor[p], pv.cap_per_part);
-    const u32 start = chunk * kScatterTile;
-    if (start >= cnt) return;
-    const u64 *keys = pv.keys + (size_t)p * pv.cap_per_part;
+    const u32 p = blockIdx.x / pv.num_ctas;
+    const u32 c = blockIdx.x - p * pv.num_ctas;
+    const size_t seg = (size_t)c * kParts + p;
+    const u32 cnt = pv.seg_count[seg];
+    const u64 *keys = pv.keys + seg * pv.seg_cap;
     const u64 top = (u64)p << 56;
-    u64 k[R];
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-        const u32 i = start + j * kThreads + threadIdx.x;
-        k[j] = i < cnt ? keys[i] : 0ull;
-    }
     u32 my_new = 0;
+    for (u32 i0 = 0; i0 < cnt; i0 += kThreads * kCountKeysPerThread) {
+        u64 k[kCountKeysPerThread];
 #pragma unroll
-    for (int j = 0; j < R; j++) {
-        if (k[j] == 0) continue;
-        bool is_new = false;
-        insert64_hashed(t, top | (k[j] & kMask56), k[j], 1ull, is_new);
-        my_new += is_new ? 1u : 0u;
+        for (int j = 0; j < kCountKeysPerThread; j++) {
+            const u32 i = i0 + j * kThreads + threadIdx.x;
+            k[j] = i < cnt ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < kCountKeysPerThread; j++) {
+            if (k[j] == 0) continue;
+            bool is_new = false;
+            insert64_hashed(t, top | (k[j] & kMask56), k[j], 1ull, is_new);
+            my_new += is_new ? 1u : 0u;
+        }
     }
     block_add_new(t, my_new, s_new);
 }
@@ -410,30 +409,41 @@ static bool use_deferred(const ssq_counter *c, int64_t n) {
     return table_bytes > kDirectTableBytes && n >= ((int64_t)1 << c->log2_cap) / 4;
 }
 
-// Size the partition buffers for a pass of n keys and reset the cursors.
-static int prepare_parts(ssq_counter *c, int64_t n, PartView *pv) {
+int scatter_grid(ssq_ctx *ctx, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
+
+// Size the partition buffers for a pass of n keys scattered by `grid` persistent CTAs.
+static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     ssq_ctx *ctx = c->ctx;
-    int64_t per = n / kParts + n / (kParts * 32) + 4096;     // mean + 3 % + slack (overflow is handled, not fatal)
-    per = (per + 255) & ~(int64_t)255;
-    if (per > c->part_cap) {
+    // a CTA sees ~n/grid keys, 1/256 of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
+    int64_t per = n / ((int64_t)grid * kParts);
+    per = per + per / 16 + 64;
+    per = (per + 3) & ~(int64_t)3;
+    const int64_t need = per * grid * kParts;
+    if (need > c->part_cap) {
         SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
         if (c->part_keys) SSQ_CUDA(cudaFree(c->part_keys));
         c->part_keys = nullptr;
         c->part_cap = 0;
-        SSQ_CUDA(cudaMalloc(&c->part_keys, sizeof(u64) * (size_t)per * kParts));
-        c->part_cap = per;
+        SSQ_CUDA(cudaMalloc(&c->part_keys, sizeof(u64) * (size_t)need));
+        c->part_cap = need;
     }
-    if (!c->part_cursor) SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * kParts));
-    SSQ_CUDA(cudaMemsetAsync(c->part_cursor, 0, sizeof(u32) * kParts, ctx->stream));
+    if (grid > c->part_ctas) {
+        SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (c->part_cursor) SSQ_CUDA(cudaFree(c->part_cursor));
+        c->part_cursor = nullptr;
+        c->part_ctas = 0;
+        SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * (size_t)grid * kParts));
+        c->part_ctas = grid;
+    }
     pv->keys = c->part_keys;
-    pv->cursor = c->part_cursor;
-    pv->cap_per_part = (u32)per;
+    pv->seg_count = c->part_cursor;
+    pv->seg_cap = (u32)per;
+    pv->num_ctas = (u32)grid;
     return SSQ_OK;
 }
 
 static int launch_count_parts(ssq_counter *c, const PartView &pv) {
-    const u32 bpp = (pv.cap_per_part + kScatterTile - 1) / kScatterTile;
-    count_parts_kernel<<<kParts * bpp, kThreads, 0, c->ctx->stream>>>(view_of(c), pv, bpp);
+    count_parts_kernel<<<kParts * pv.num_ctas, kThreads, 0, c->ctx->stream>>>(view_of(c), pv);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -460,18 +470,26 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
                                      words + (size_t)p * W, lens + p, view_of(c), PartView{}, stop);
         });
     int rc;
+    SSQ_CUDA(cudaEventRecord(c->ev[0], ctx->stream));
     if (use_deferred(c, n)) {
+        c->last_pass_phases = 2;
         PartView pv;
-        rc = prepare_parts(c, n, &pv);
+        int sgrid = scatter_grid(ctx, n);
+        if ((int64_t)sgrid * 65536 > n) sgrid = (int)(n / 65536 > 0 ? n / 65536 : 1);   // keep the segments from being mostly padding
+        rc = prepare_parts(c, n, sgrid, &pv);
         if (rc) return rc;
         rc = launch_pack_count(ctx, c->klass, true, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c), pv, nullptr);
         if (rc) return rc;
+        SSQ_CUDA(cudaEventRecord(c->ev[1], ctx->stream));
         rc = launch_count_parts(c, pv);
     } else {
+        c->last_pass_phases = 1;
         rc = launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c),
                                PartView{}, nullptr);
+        SSQ_CUDA(cudaEventRecord(c->ev[1], ctx->stream));
     }
     if (rc) return rc;
+    SSQ_CUDA(cudaEventRecord(c->ev[2], ctx->stream));
     return finish_pass(c);
 }
 
@@ -499,6 +517,9 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->part_keys = nullptr;
     c->part_cursor = nullptr;
     c->part_cap = 0;
+    c->part_ctas = 0;
+    c->last_pass_phases = 0;
+    for (int i = 0; i < 3; i++) SSQ_CUDA(cudaEventCreate(&c->ev[i]));
     const size_t bytes = ((size_t)1 << c->log2_cap) * slot_bytes(klass);
     SSQ_CUDA(cudaMalloc(&c->slots, bytes));
     SSQ_CUDA(cudaMalloc(&c->d_size, 4 * sizeof(u64)));
@@ -519,6 +540,7 @@ int ssq_counter_destroy(ssq_counter *c) {
     cudaFree(c->first_idx);
     cudaFree(c->part_keys);
     cudaFree(c->part_cursor);
+    for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_size);
     cudaFreeHost(c->h_size);
     delete c;
@@ -546,9 +568,9 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
         int rc = SSQ_OK;
         if (counts == nullptr && use_deferred(c, n)) {
             PartView pv;
-            rc = prepare_parts(c, n, &pv);
+            int grid = grid_for(ctx, (n + 65535) / 65536, 8);
+            rc = prepare_parts(c, n, grid, &pv);
             if (rc) return rc;
-            int grid = grid_for(ctx, (n + kScatterTile - 1) / kScatterTile, 6);
             scatter_packed_kernel<<<grid, kThreads, 0, ctx->stream>>>(view_of(c), pv, (const u64 *)words, lens, n, 0);
             SSQ_LAUNCH_CHECK();
             rc = launch_count_parts(c, pv);
@@ -641,6 +663,17 @@ int ssq_counter_size(ssq_counter *c, int64_t *n_unique) {
     SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, c->ctx->stream));
     SSQ_CUDA(cudaStreamSynchronize(c->ctx->stream));
     *n_unique = (int64_t)*c->h_size;
+    return SSQ_OK;
+}
+
+int ssq_counter_last_pass_ms(ssq_counter *c, float *phase1_ms, float *phase2_ms) {
+    SSQ_ARG(c != nullptr && phase1_ms != nullptr && phase2_ms != nullptr, "NULL argument");
+    *phase1_ms = *phase2_ms = 0.0f;
+    if (c->last_pass_phases == 0) return SSQ_OK;
+    DeviceGuard g(c->ctx->device);
+    SSQ_CUDA(cudaEventSynchronize(c->ev[2]));
+    SSQ_CUDA(cudaEventElapsedTime(phase1_ms, c->ev[0], c->ev[1]));
+    SSQ_CUDA(cudaEventElapsedTime(phase2_ms, c->ev[1], c->ev[2]));
     return SSQ_OK;
 }
 

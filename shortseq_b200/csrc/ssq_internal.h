@@ -29,8 +29,11 @@ struct ssq_counter {
     ssq::u64 *h_gate;     // pinned
     int64_t expected_unique;   // caller's bound on the distinct keys (0 = unknown: conservative gated inserts)
     ssq::u64 *part_keys;       // partition buffers of the deferred-insert path (lazily sized)
-    ssq::u32 *part_cursor;     // [kParts]
-    int64_t part_cap;          // entries per partition currently allocated
+    ssq::u32 *part_cursor;     // [part_ctas][kParts] segment fill counts
+    int64_t part_cap;          // key entries currently allocated
+    int part_ctas;             // scatter CTAs the count array is sized for
+    cudaEvent_t ev[3];         // start / end of phase 1 / end of phase 2 of the last bounded pass
+    int last_pass_phases;      // 0 none, 1 direct single kernel, 2 deferred (scatter + count)
 };
 
 namespace ssq {

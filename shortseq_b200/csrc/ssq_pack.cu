@@ -18,10 +18,11 @@
 //
 // Counting modes of the fixed-class kernel:
 //   kModeDirect   insert each key straight into the table (tables that fit in L2),
-//   kModeScatter  append each key's 64-bit table key to one of 256 hash partitions
-//                 (block-level histogram in shared memory -> one global cursor bump per
-//                 partition per tile), so that ssq_counter.cu can insert partition by
-//                 partition with the table region resident in L2.
+//   kModeScatter  append each key's 64-bit table key to one of 256 hash partitions -- every
+//                 persistent CTA owns a private segment of every partition, so the append is a
+//                 shared-memory cursor bump and an 8-byte store, no global atomics -- so that
+//                 ssq_counter.cu can insert partition by partition with the table region
+//                 resident in L2.
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
 
@@ -63,42 +64,60 @@ __device__ __noinline__ uint4 load_chunk_guarded(const uint8_t *ascii, int64_t l
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Stage 1.  Encodes the 16-byte chunks covering bytes [t0, t1) into codes[]; chunk c covers the 16
-// bytes from byte index a0 + 16c, a0 = t0 rounded down to a 16-byte ADDRESS boundary.  `lead`
-// receives t0 - a0.  Bytes of neighbouring tiles that share the edge chunks are encoded and
-// validated too: their codes are never extracted, and a stray invalid byte there merely sends this
-// tile through the exact per-read re-check.  `pad` extra words after the last chunk are zeroed.
-// The caller must __syncthreads().
-template <int THREADS>
-__device__ __forceinline__ void encode_tile(const uint8_t *ascii, int64_t lo, int64_t hi, int64_t t0, int tile_bytes,
-                                            u32 *codes, int pad, u32 &bad, int &lead) {
+// Geometry of one tile's byte range [t0, t0 + tile_bytes): chunk c covers the 16 bytes from byte index
+// a0 + 16c, a0 = t0 rounded down to a 16-byte ADDRESS boundary, lead = t0 - a0.  Bytes of neighbouring
+// tiles that share the edge chunks are encoded and validated too: their codes are never extracted, and a
+// stray invalid byte there merely sends this tile through the exact per-read re-check.
+struct TileGeom {
+    const uint8_t *src;   // ascii + a0 (16-byte aligned address)
+    int64_t a0;
+    int nchunks;
+    int lead;
+    bool interior;        // every chunk lies inside [lo, hi): loads need no guard
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const uint8_t *ascii, int64_t lo, int64_t hi, int64_t t0, int tile_bytes) {
+    TileGeom g;
     const int mis = (int)((uintptr_t)ascii & 15);
-    lead = (int)((t0 + mis) & 15);
-    const int64_t a0 = t0 - lead;
-    const int nchunks = (tile_bytes + lead + 15) >> 4;
-    const uint8_t *src = ascii + a0;
-    if (a0 >= lo && a0 + 16 * (int64_t)nchunks <= hi) {          // whole sweep inside the buffer: no guards
-        for (int c0 = threadIdx.x; c0 < nchunks; c0 += THREADS * kLoadUnroll) {
-            uint4 v[kLoadUnroll];
+    g.lead = (int)((t0 + mis) & 15);
+    g.a0 = t0 - g.lead;
+    g.nchunks = (tile_bytes + g.lead + 15) >> 4;
+    g.src = ascii + g.a0;
+    g.interior = g.a0 >= lo && g.a0 + 16 * (int64_t)g.nchunks <= hi;
+    return g;
+}
+
+// Issue the first kLoadUnroll rounds of 16-byte loads of an interior tile (results land in v[]).
+template <int THREADS>
+__device__ __forceinline__ void issue_tile_loads(const TileGeom &g, uint4 (&v)[kLoadUnroll]) {
 #pragma unroll
-            for (int j = 0; j < kLoadUnroll; j++) {
-                int c = c0 + j * THREADS;
-                if (c < nchunks) v[j] = ld_stream_v4(src + 16 * c);
-            }
+    for (int j = 0; j < kLoadUnroll; j++) {
+        const int c = threadIdx.x + j * THREADS;
+        if (c < g.nchunks) v[j] = ld_stream_v4(g.src + 16 * c);
+    }
+}
+
+// Stage 1: codes[c] = 2-bit codes of chunk c.  `v` holds the prefetched first rounds when `prefetched`.
+// `pad` extra words after the last chunk are zeroed.  The caller must __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ void encode_tile(const uint8_t *ascii, int64_t lo, int64_t hi, const TileGeom &g, bool prefetched,
+                                            const uint4 (&v)[kLoadUnroll], u32 *codes, int pad, u32 &bad) {
+    if (prefetched) {
 #pragma unroll
-            for (int j = 0; j < kLoadUnroll; j++) {
-                int c = c0 + j * THREADS;
-                if (c < nchunks) codes[c] = encode16(v[j], bad);
-            }
+        for (int j = 0; j < kLoadUnroll; j++) {
+            const int c = threadIdx.x + j * THREADS;
+            if (c < g.nchunks) codes[c] = encode16(v[j], bad);
         }
+        for (int c = threadIdx.x + kLoadUnroll * THREADS; c < g.nchunks; c += THREADS)   // long tiles (ShortSeq192)
+            codes[c] = encode16(ld_stream_v4(g.src + 16 * c), bad);
     } else {                                                     // first / last tile of the buffer
-        for (int c = threadIdx.x; c < nchunks; c += THREADS) {
-            int64_t idx = a0 + 16 * (int64_t)c;
-            uint4 v = (idx >= lo && idx + 16 <= hi) ? ld_stream_v4(ascii + idx) : load_chunk_guarded(ascii, lo, hi, idx);
-            codes[c] = encode16(v, bad);
+        for (int c = threadIdx.x; c < g.nchunks; c += THREADS) {
+            const int64_t idx = g.a0 + 16 * (int64_t)c;
+            uint4 x = (idx >= lo && idx + 16 <= hi) ? ld_stream_v4(ascii + idx) : load_chunk_guarded(ascii, lo, hi, idx);
+            codes[c] = encode16(x, bad);
         }
     }
-    if ((int)threadIdx.x < pad) codes[nchunks + threadIdx.x] = 0;
+    if ((int)threadIdx.x < pad) codes[g.nchunks + threadIdx.x] = 0;
 }
 
 // 64 bits of the code stream starting at bit `bit` (even, >= 0) of codes[].
@@ -130,7 +149,35 @@ __device__ __noinline__ void report_len(DevReport *rep, int64_t len, u64 idx) {
     else atomicMin(&rep->first_bad_len, idx);
 }
 
+// Offsets of one tile, held in registers so that the next tile's can be in flight during this one.
+struct TileOffsets {
+    int64_t t0, t1;
+    int64_t start[kRPT];
+    int nreads;
+};
+
+__device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets, int64_t n, int64_t tile) {
+    TileOffsets o;
+    const int64_t first = tile * kTileReads;
+    o.nreads = first < n ? (int)min((int64_t)kTileReads, n - first) : 0;
+    o.t0 = o.t1 = 0;
+#pragma unroll
+    for (int k = 0; k < kRPT; k++) o.start[k] = 0;
+    if (o.nreads > 0) {
+        o.t0 = offsets[first];
+        o.t1 = offsets[first + o.nreads];
+#pragma unroll
+        for (int k = 0; k < kRPT; k++) {
+            const int r = threadIdx.x + k * kPackThreads;
+            if (r < o.nreads) o.start[k] = offsets[first + r];
+        }
+    }
+    return o;
+}
+
 // ---- ShortSeq64 / ShortSeq192 ------------------------------------------------------------------
+// Persistent CTAs walk the tiles with a grid stride.  The loop is software-pipelined: while a tile is being
+// extracted, the 16-byte loads of the CTA's next tile and the offsets of the one after are already in flight.
 template <int KLASS, int MODE>
 __global__ void __launch_bounds__(kPackThreads) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     constexpr int MAXLEN = KLASS == SSQ_CLASS_64 ? 32 : 96;
@@ -142,119 +189,130 @@ __global__ void __launch_bounds__(kPackThreads) pack_fixed_kernel(PackArgs a, Ta
     __shared__ u32 codes[MAX_CHUNKS + PAD];
     __shared__ u32 srel[kTileReads + 1];                // read starts relative to the tile start
     __shared__ u32 s_new[kPackThreads / 32];
-    __shared__ u32 hist[MODE == kModeScatter ? 2 * kParts : 1];
-    __shared__ u32 pbase[MODE == kModeScatter ? kParts : 1];
+    // scatter mode: per-partition staging of this CTA (see ssq_table.cuh)
+    __shared__ __align__(16) u64 stage[MODE == kModeScatter ? kParts * kStageCap : 1];
+    __shared__ u32 scnt[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 sgcur[MODE == kModeScatter ? kParts : 1];
+    static_assert(kPackThreads == kParts, "thread p owns partition p's staging");
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;
-    if (MODE == kModeScatter) {
-        for (int p = threadIdx.x; p < 2 * kParts; p += kPackThreads) hist[p] = 0;
-        __syncthreads();
-    }
+    if (MODE == kModeScatter)
+        for (int p = threadIdx.x; p < kParts; p += kPackThreads) { scnt[p] = 0; sgcur[p] = 0; }   // ordered by the first tile's barrier
 
     u32 my_new = 0;
-    int flip = 0;
     const int64_t ntiles = (a.n + kTileReads - 1) / kTileReads;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    int64_t tile = blockIdx.x;
+
+    // prologue: this tile's offsets and loads, the next tile's offsets
+    TileOffsets cur = load_tile_offsets(a.offsets, a.n, tile);
+    bool cur_ok = cur.nreads > 0 && cur.t0 >= a.lo && cur.t1 >= cur.t0 && cur.t1 <= a.hi &&
+                  (cur.t1 - cur.t0) <= (int64_t)kTileReads * MAXLEN;
+    TileGeom geom = tile_geom(a.ascii, a.lo, a.hi, cur.t0, cur_ok ? (int)(cur.t1 - cur.t0) : 0);
+    uint4 v[kLoadUnroll];
+    bool prefetched = cur_ok && geom.interior;
+    if (prefetched) issue_tile_loads<kPackThreads>(geom, v);
+    TileOffsets nxt = load_tile_offsets(a.offsets, a.n, tile + stride);
+
+    for (; tile < ntiles; tile += stride) {
         const int64_t first = tile * kTileReads;
-        const int nreads = (int)min((int64_t)kTileReads, a.n - first);
-        const int64_t t0 = a.offsets[first];
-        const int64_t t1 = a.offsets[first + nreads];
-        // a tile whose byte range is inconsistent or larger than the staging buffer holds a read of the
-        // wrong class (or offsets outside the buffer): report per read, pack nothing
-        const bool tile_ok = t0 >= a.lo && t1 >= t0 && t1 <= a.hi && (t1 - t0) <= (int64_t)kTileReads * MAXLEN;
+        const int nreads = cur.nreads;
+        const int64_t t0 = cur.t0;
+        const int tile_bytes = cur_ok ? (int)(cur.t1 - cur.t0) : 0;
+        const int lead = geom.lead;
+        u32 bad = 0;
+        if (cur_ok) {
 #pragma unroll
-        for (int k = 0; k < kRPT; k++) {
-            const int r = threadIdx.x + k * kPackThreads;
-            if (r < nreads) {
-                const int64_t o = a.offsets[first + r];
-                if (tile_ok) {
-                    // out-of-tile starts become an impossible value that fails the checks below
-                    srel[r] = (o >= t0 && o <= t1) ? (u32)(o - t0) : 0xFFFFFFFFu;
-                } else {
-                    const int64_t len = a.offsets[first + r + 1] - o;
+            for (int k = 0; k < kRPT; k++) {
+                const int r = threadIdx.x + k * kPackThreads;
+                // out-of-tile starts become an impossible value that fails the checks below
+                if (r < nreads) srel[r] = (cur.start[k] >= t0 && cur.start[k] <= cur.t1) ? (u32)(cur.start[k] - t0) : 0xFFFFFFFFu;
+            }
+            if (threadIdx.x == 0) srel[nreads] = (u32)tile_bytes;
+            encode_tile<kPackThreads>(a.ascii, a.lo, a.hi, geom, prefetched, v, codes, PAD, bad);
+        } else {
+            // a tile whose byte range is inconsistent or larger than the staging buffer holds a read of the wrong
+            // class (or offsets outside the buffer): report per read, pack nothing
+#pragma unroll
+            for (int k = 0; k < kRPT; k++) {
+                const int r = threadIdx.x + k * kPackThreads;
+                if (r < nreads) {
+                    const int64_t len = a.offsets[first + r + 1] - cur.start[k];
                     if (len < MINLEN || len > MAXLEN) report_len(a.rep, len, (u64)(a.index_base + first + r));
                 }
             }
-        }
-        if (!tile_ok) {
-            if (threadIdx.x == 0 && (t0 < a.lo || t1 > a.hi || t1 < t0))
+            if (threadIdx.x == 0 && (t0 < a.lo || cur.t1 > a.hi || cur.t1 < t0))
                 atomicMin(&a.rep->first_bad_len, (u64)(a.index_base + first));
-            continue;
         }
-        const int tile_bytes = (int)(t1 - t0);
-        if (threadIdx.x == 0) srel[nreads] = (u32)tile_bytes;
-        u32 bad = 0;
-        int lead;
-        encode_tile<kPackThreads>(a.ascii, a.lo, a.hi, t0, tile_bytes, codes, PAD, bad, lead);
+
+        // ---- prefetch: the next tile's bytes, the offsets of the tile after it
+        const bool nxt_ok = nxt.nreads > 0 && nxt.t0 >= a.lo && nxt.t1 >= nxt.t0 && nxt.t1 <= a.hi &&
+                            (nxt.t1 - nxt.t0) <= (int64_t)kTileReads * MAXLEN;
+        const TileGeom ngeom = tile_geom(a.ascii, a.lo, a.hi, nxt.t0, nxt_ok ? (int)(nxt.t1 - nxt.t0) : 0);
+        const bool nprefetched = nxt_ok && ngeom.interior;
+        if (nprefetched) issue_tile_loads<kPackThreads>(ngeom, v);
+        const TileOffsets nxt2 = load_tile_offsets(a.offsets, a.n, tile + 2 * stride);
+
         const int tile_bad = __syncthreads_or(bad != 0);
 
-        u64 key[kRPT];
-        u32 rank[kRPT], part[kRPT];
-        bool ok[kRPT];
-        u32 *h = hist + flip * kParts;
-#pragma unroll
-        for (int k = 0; k < kRPT; k++) {
-            const int r = threadIdx.x + k * kPackThreads;
-            ok[k] = false;
-            if (r >= nreads) continue;
-            const int64_t i = first + r;
-            const u32 r0 = srel[r], r1 = srel[r + 1];
-            const int len = (int)(r1 - r0);
-            const bool len_ok = r0 <= (u32)tile_bytes && r1 <= (u32)tile_bytes && len >= MINLEN && len <= MAXLEN;
-            u64 w[W];
-            if (len_ok) {
-                const int bit = 2 * ((int)r0 + lead);
-#pragma unroll
-                for (int j = 0; j < W; j++) w[j] = keep_bits(extract64(codes, bit + 64 * j), 2 * len - 64 * j);
-                ok[k] = !(tile_bad && read_has_bad_base(a.ascii + t0 + r0, len));
-                if (!ok[k]) atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + i));
-            } else {
-#pragma unroll
-                for (int j = 0; j < W; j++) w[j] = 0;
-                report_len(a.rep, (int64_t)a.offsets[i + 1] - a.offsets[i], (u64)(a.index_base + i));
-            }
-#pragma unroll
-            for (int j = 0; j < W; j++) a.words[(size_t)i * W + j] = w[j];
-            ((uint8_t *)a.lens)[i] = len_ok ? (uint8_t)len : 0;
-            if (MODE == kModeDirect && ok[k]) {
-                bool is_new = false;
-                if constexpr (KLASS == SSQ_CLASS_64) insert64(t, w[0], (u32)len, 1ull, is_new);
-                else insert192(t, w[0], w[1], w[2], (u32)len, 1ull, is_new);
-                my_new += is_new ? 1u : 0u;
-            }
-            if (MODE == kModeScatter && ok[k]) {
-                const u64 h2 = rotl64(mix64(w[0]), t.rot);
-                key[k] = key64_of(h2, (u32)len);
-                part[k] = (u32)(h2 >> 56);
-                rank[k] = atomicAdd(&h[part[k]], 1u);
-            }
-        }
-        if (MODE == kModeScatter) {
-            __syncthreads();
-            // one cursor bump per non-empty partition per tile; the other histogram is cleared for the next tile
-            for (int p = threadIdx.x; p < kParts; p += kPackThreads) {
-                const u32 cnt = h[p];
-                pbase[p] = cnt ? atomicAdd(&pv.cursor[p], cnt) : 0u;
-                hist[(flip ^ 1) * kParts + p] = 0;
-            }
-            __syncthreads();
+        if (cur_ok) {
 #pragma unroll
             for (int k = 0; k < kRPT; k++) {
-                if (!ok[k]) continue;
-                const u32 pos = pbase[part[k]] + rank[k];
-                if (pos < pv.cap_per_part) {
-                    pv.keys[(size_t)part[k] * pv.cap_per_part + pos] = key[k];
-                } else {                                   // partition buffer full: count it right away
+                const int r = threadIdx.x + k * kPackThreads;
+                const int64_t i = first + r;
+                u64 w[W];
+                bool ok = false;
+                int len = 0;
+                if (r < nreads) {
+                    const u32 r0 = srel[r], r1 = srel[r + 1];
+                    len = (int)(r1 - r0);
+                    const bool len_ok = r0 <= (u32)tile_bytes && r1 <= (u32)tile_bytes && len >= MINLEN && len <= MAXLEN;
+                    if (len_ok) {
+                        const int bit = 2 * ((int)r0 + lead);
+#pragma unroll
+                        for (int j = 0; j < W; j++) w[j] = keep_bits(extract64(codes, bit + 64 * j), 2 * len - 64 * j);
+                        ok = !(tile_bad && read_has_bad_base(a.ascii + t0 + r0, len));
+                        if (!ok) atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + i));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < W; j++) w[j] = 0;
+                        report_len(a.rep, (int64_t)a.offsets[i + 1] - a.offsets[i], (u64)(a.index_base + i));
+                    }
+#pragma unroll
+                    for (int j = 0; j < W; j++) a.words[(size_t)i * W + j] = w[j];
+                    ((uint8_t *)a.lens)[i] = len_ok ? (uint8_t)len : 0;
+                }
+                if (MODE == kModeDirect && ok) {
                     bool is_new = false;
-                    const u64 h2 = ((u64)part[k] << 56) | (key[k] & kMask56);
-                    insert64_hashed(t, h2, key[k], 1ull, is_new);
+                    if constexpr (KLASS == SSQ_CLASS_64) insert64(t, w[0], (u32)len, 1ull, is_new);
+                    else insert192(t, w[0], w[1], w[2], (u32)len, 1ull, is_new);
                     my_new += is_new ? 1u : 0u;
                 }
+                if constexpr (MODE == kModeScatter) {
+                    if (ok) {
+                        // stage the table key for its hash partition
+                        const u64 h2 = rotl64(mix64(w[0]), t.rot);
+                        const u64 key = key64_of(h2, (u32)len);
+                        if (!stage_key(stage, scnt, (u32)(h2 >> 56), key)) {   // staging full: count it right away
+                            bool is_new = false;
+                            insert64_hashed(t, h2, key, 1ull, is_new);
+                            my_new += is_new ? 1u : 0u;
+                        }
+                    }
+                }
             }
-            flip ^= 1;
-        } else {
-            __syncthreads();   // codes[] / srel[] are rewritten by the next tile
+            if constexpr (MODE == kModeScatter) {
+                __syncthreads();
+                flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, false, my_new);
+            }
         }
+        __syncthreads();   // codes[] / srel[] are rewritten by the next tile
+
+        cur = nxt; cur_ok = nxt_ok; geom = ngeom; prefetched = nprefetched; nxt = nxt2;
+    }
+    if constexpr (MODE == kModeScatter) {
+        flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, true, my_new);   // the loop ended with a barrier
+        pv.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = sgcur[threadIdx.x];
     }
     if (MODE != kModePack) {
         // one size update per CTA: a single global counter cannot take one atomic per warp
@@ -296,8 +354,11 @@ __global__ void __launch_bounds__(kPackThreads) pack_var_kernel(PackArgs a) {
             continue;
         }
         u32 bad = 0;
-        int lead;
-        encode_tile<kPackThreads>(a.ascii, a.lo, a.hi, t0, (int)(t1 - t0), codes, PAD, bad, lead);
+        const TileGeom geom = tile_geom(a.ascii, a.lo, a.hi, t0, (int)(t1 - t0));
+        const int lead = geom.lead;
+        uint4 v[kLoadUnroll];
+        if (geom.interior) issue_tile_loads<kPackThreads>(geom, v);
+        encode_tile<kPackThreads>(a.ascii, a.lo, a.hi, geom, geom.interior, v, codes, PAD, bad);
         const int tile_bad = __syncthreads_or(bad != 0);
         for (int r = warp; r < nreads; r += kPackThreads / 32) {
             const int64_t i = first + r;
@@ -322,15 +383,26 @@ __global__ void __launch_bounds__(kPackThreads) pack_var_kernel(PackArgs a) {
     }
 }
 
+// Persistent grid: exactly as many CTAs as are resident at once (one wave), capped by the number of tiles.
 template <int KLASS, int MODE>
-static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop) {
+static int fixed_grid(ssq_ctx *ctx, int64_t n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_fixed_kernel<KLASS, MODE>, kPackThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    return grid_for(ctx, (n + kTileReads - 1) / kTileReads, per_sm);
+}
+
+template <int KLASS, int MODE>
+static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid = 0) {
     if (a.n <= 0) return SSQ_OK;
-    int64_t ntiles = (a.n + kTileReads - 1) / kTileReads;
-    int grid = grid_for(ctx, ntiles, 6);
+    if (grid <= 0) grid = fixed_grid<KLASS, MODE>(ctx, a.n);
     pack_fixed_kernel<KLASS, MODE><<<grid, kPackThreads, 0, ctx->stream>>>(a, t, pv, stop);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
+
+// grid of the scatter-mode launch for n reads: it fixes the segment layout of the partition buffers
+int scatter_grid(ssq_ctx *ctx, int64_t n) { return fixed_grid<SSQ_CLASS_64, kModeScatter>(ctx, n); }
 
 // used by ssq_counter.cu: fused pack + (direct insert | partition scatter)
 int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *ascii, int64_t lo, int64_t hi,
@@ -338,7 +410,7 @@ int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *asci
                       const TableView &t, const PartView &pv, const u64 *stop) {
     PackArgs a{ascii, lo, hi, offsets, n, index_base, words, lens, nullptr, ctx->d_report};
     if (klass == SSQ_CLASS_64)
-        return scatter ? launch_fixed<SSQ_CLASS_64, kModeScatter>(ctx, a, t, pv, stop)
+        return scatter ? launch_fixed<SSQ_CLASS_64, kModeScatter>(ctx, a, t, pv, stop, (int)pv.num_ctas)
                        : launch_fixed<SSQ_CLASS_64, kModeDirect>(ctx, a, t, pv, stop);
     return launch_fixed<SSQ_CLASS_192, kModeDirect>(ctx, a, t, pv, stop);
 }
