@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libshortseq_b200.so")
+LIB_PATH = os.environ.get("SSQ_LIB") or os.path.join(HERE, "libshortseq_b200.so")
 
 OK, ERR_BAD_BASE, ERR_TOO_LONG, ERR_CLASS, ERR_CUDA, ERR_LEN_MISMATCH, ERR_TABLE_FULL, ERR_ARG = range(8)
 CLASS_64, CLASS_192, CLASS_VAR = 0, 1, 2

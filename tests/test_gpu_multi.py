@@ -1,0 +1,61 @@
+"""GPU, multi-rank: the hash-partitioned all-to-all merge over NCCL (needs >= 2 GPUs; skipped otherwise)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, klass, out_dir):
+    import torch.distributed as dist
+    import shortseq_b200 as sq
+    from shortseq_b200.distributed import global_size, merge_alltoall
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        lo, hi = (18, 32) if klass == 0 else (40, 96)
+        b = sq.synth_reads(300_000, 40_000, lo, hi, seed=0x5EED0001, first_read=rank * 300_000)
+        local = sq.DeviceCounter(klass, expected_unique=50_000)
+        local.pack_count(b)
+        owner = merge_alltoall(local)
+        total = global_size(owner)
+        keys, counts, _, _ = owner.export(1)
+        w, l, _ = keys.to_host()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), w=w, l=l, c=counts.cpu().numpy(), total=total)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("klass", [0, 1])
+def test_multi_gpu_merge_matches_oracle(tmp_path, klass, oracle):
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from shortseq_b200 import hashing
+    mp.spawn(_worker, args=(world, _free_port(), klass, str(tmp_path)), nprocs=world, join=True)
+    lo, hi = (18, 32) if klass == 0 else (40, 96)
+    buf, off = oracle.synth_reads(0x5EED0001, 0, 600_000, 40_000, lo, hi)
+    ow, ol, _ = oracle.pack_batch(klass, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 1 if klass == 0 else 3)
+    expect = {(int(ul[j]), tuple(np.atleast_1d(uw[j]).tolist())): int(uc[j]) for j in range(len(ul))}
+    merged = {}
+    for r in range(world):
+        d = np.load(tmp_path / f"r{r}.npz")
+        assert int(d["total"]) == len(expect)
+        assert (hashing.owner_rank(d["w"], d["l"], klass, world) == r).all()
+        for j in range(len(d["l"])):
+            key = (int(d["l"][j]), tuple(np.atleast_1d(d["w"][j]).tolist()))
+            assert key not in merged
+            merged[key] = int(d["c"][j])
+    assert merged == expect
