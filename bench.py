@@ -12,9 +12,9 @@ hash-partitioned all-to-all merge into per-rank owner tables; the step ends with
 of the number of distinct keys.
 
   value     whole-job Gbases/s with the reads resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the host-buffer C-ABI call ssq_host_pack_count: pinned host ASCII+offsets
-            in, packed words+lens out, host<->device copies inside the timed region (a bounded slice of
-            the workload, size in e2e.reads_per_step)
+  e2e       same metric through the host-buffer C-ABI call ssq_host_pack_count_lens: pinned host ASCII + one
+            uint8 length per read in, packed words out, host<->device copies inside the timed region (a
+            bounded slice of the workload, size in e2e.reads_per_step)
   roofline  fused pack+count kernel: algorithmic bytes (L+8+8W+1 per read + 8W+9 per unique)
             / CUDA-event time of its launches, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference: the unmodified reference (oracle/_ref, Cython) on the host cores
@@ -369,10 +369,9 @@ def run_ours(args):
         ue = max(1, int(ne / (n / u)))
         eb = sq.synth_reads(ne, ue, L, L, seed=SEED, first_read=rank * ne)
         h_ascii = torch.empty(ne * L, dtype=torch.uint8).pin_memory()
-        h_off = torch.empty(ne + 1, dtype=torch.int64).pin_memory()
-        h_ascii.copy_(eb.ascii[: ne * L]); h_off.copy_(eb.offsets)
+        h_ascii.copy_(eb.ascii[: ne * L])
+        h_lens = torch.full((ne,), L, dtype=torch.uint8).pin_memory()      # one length per read, as a list of bytes carries
         h_words = torch.empty((ne,) if W == 1 else (ne, 3), dtype=torch.int64).pin_memory()
-        h_lens = torch.empty(ne, dtype=torch.uint8).pin_memory()
         del eb
         ectr = sq.DeviceCounter(klass, expected_unique=ue)
         eowner = sq.DeviceCounter(klass, expected_unique=2 * ue // world, hash_rot=world.bit_length() - 1) if world > 1 else None
@@ -380,8 +379,8 @@ def run_ours(args):
 
         def estep():
             _lib.check(lib.ssq_counter_clear(ectr.handle))
-            _lib.check(lib.ssq_host_pack_count(h, ectr.handle, h_ascii.data_ptr(), h_off.data_ptr(), ne, h_words.data_ptr(),
-                                               h_lens.data_ptr(), 1 << 22, C.byref(rep)))
+            _lib.check(lib.ssq_host_pack_count_lens(h, ectr.handle, h_ascii.data_ptr(), h_lens.data_ptr(), ne, h_words.data_ptr(),
+                                                    1 << 22, C.byref(rep)))
             assert rep.code == 0
             if world > 1:
                 _lib.check(lib.ssq_counter_clear(eowner.handle))
@@ -402,9 +401,10 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         e2e = {"value": round(world * ne * L / (e_ms * 1e-3) / 1e9, 3), "unit": "Gbases/s",
-               "h2d_bytes_per_step": ne * L + 8 * (ne + 1), "d2h_bytes_per_step": ne * (8 * W + 1) + 8,
+               "h2d_bytes_per_step": ne * L + ne, "d2h_bytes_per_step": ne * 8 * W + 8,
                "reads_per_step": ne, "ms_per_step": round(e_ms, 3),
-               "call": "ssq_host_pack_count (pinned host ASCII+offsets in, packed words+lens out, 4M-read chunks)"}
+               "call": "ssq_host_pack_count_lens (pinned host ASCII + one uint8 length per read in, packed words out, "
+                       "4M-read chunks, H2D / kernel / D2H overlapped on three streams)"}
 
     if rank == 0:
         line = {

@@ -195,6 +195,12 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
 int ssq_host_pack_count(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii,
                         const int64_t *h_offsets, int64_t n, uint64_t *h_words, uint8_t *h_lens,
                         int64_t chunk_reads, ssq_report *report);
+/* Same pipeline with the read boundaries given as one uint8 length per read (what a list of bytes objects
+ * carries; reads of the countable classes are <= 96 nt): 1 instead of 8 bytes per read cross PCIe, the offsets
+ * are scanned on the device, and only the packed words come back (the caller already holds the lengths).
+ * h_words may be NULL. */
+int ssq_host_pack_count_lens(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii, const uint8_t *h_lens,
+                             int64_t n, uint64_t *h_words, int64_t chunk_reads, ssq_report *report);
 
 /* ---- synthetic reads (measurement tooling) ----------------
  * Deterministic counter-based generator, identical to oracle/ssq_oracle.c's

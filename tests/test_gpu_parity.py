@@ -375,3 +375,37 @@ def test_counter_deferred_partition_overflow_and_growth(sq, oracle):
     kw, kl, _ = keys.to_host()
     got = counter_dict(kw, kl, counts.cpu().numpy())
     assert got == expect and max(got.values()) >= n // 2
+
+
+def test_host_pipeline_lens_variant(sq, oracle):
+    """ssq_host_pack_count_lens: boundaries as one uint8 length per read; same words and counts."""
+    import ctypes as C
+    from shortseq_b200 import _lib
+    rng = np.random.default_rng(112)
+    for klass, lo, hi in ((0, 0, 32), (1, 33, 96)):
+        pool = rand_reads(rng, 2000, lo, hi)
+        reads = [pool[i] for i in rng.integers(0, 2000, size=60_000)]
+        buf, off = concat(reads)
+        lens_in = np.diff(off).astype(np.uint8)
+        ctr = sq.DeviceCounter(klass, expected_unique=3000)
+        words = np.zeros(len(reads) if klass == 0 else (len(reads), 3), np.uint64)
+        rep = _lib.Report()
+        _lib.check(_lib.lib().ssq_host_pack_count_lens(ctr.ctx.bind(), ctr.handle, buf.ctypes.data, lens_in.ctypes.data, len(reads),
+                                                      words.ctypes.data, 7001, C.byref(rep)))
+        assert rep.code == 0
+        ow, ol, _ = oracle.pack_batch(klass, buf, off)
+        assert np.array_equal(words, ow)
+        uw, ul, uc, _ = oracle.count(ow, ol, 3 if klass == 1 else 1)
+        keys, counts, _, _ = ctr.export(1)
+        kw, kl, _ = keys.to_host()
+        assert counter_dict(kw, kl, counts.cpu().numpy()) == counter_dict(uw, ul, uc)
+    # a bad base is reported with its index in the whole batch, not in its chunk
+    reads = [b"ACGT" * 5] * 20_000
+    reads[15_000] = b"ACGTNACGTACGTACGTACG"
+    buf, off = concat(reads)
+    lens_in = np.diff(off).astype(np.uint8)
+    ctr = sq.DeviceCounter(0, expected_unique=10)
+    rep = _lib.Report()
+    _lib.check(_lib.lib().ssq_host_pack_count_lens(ctr.ctx.bind(), ctr.handle, buf.ctypes.data, lens_in.ctypes.data, len(reads), None, 4096,
+                                                  C.byref(rep)))
+    assert rep.code == _lib.ERR_BAD_BASE and rep.first_bad_read == 15_000
