@@ -257,10 +257,19 @@ __global__ void __launch_bounds__(kThreads) export_count_kernel(TableView t, int
     for (int p = threadIdx.x; p < kMaxParts; p += kThreads) cnt[p] = 0;
     __syncthreads();
     const u64 cap = 1ull << t.log2_cap;
+    // the table is hash-ordered, so a thread sees long runs of one partition: count runs locally
+    u32 run_part = 0, run = 0;
     for (u64 s = (u64)blockIdx.x * kThreads + threadIdx.x; s < cap; s += (u64)gridDim.x * kThreads) {
         Tuple r = read_slot<KLASS>(t, s, log2_parts);
-        if (r.used) atomicAdd(&cnt[r.part], 1u);
+        if (!r.used) continue;
+        if (r.part != run_part) {
+            if (run) atomicAdd(&cnt[run_part], run);
+            run_part = r.part;
+            run = 0;
+        }
+        run++;
     }
+    if (run) atomicAdd(&cnt[run_part], run);
     __syncthreads();
     for (int p = threadIdx.x; p < (1 << log2_parts); p += kThreads)
         if (cnt[p]) atomicAdd(&part_counts[p], (u64)cnt[p]);
@@ -278,6 +287,8 @@ __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, i
                                                                   int64_t *first_idx) {
     __shared__ u32 cnt[kMaxParts];
     __shared__ u64 base[kMaxParts];
+    __shared__ u32 s_part[2];
+    __shared__ u32 s_warp[kThreads / 32];
     const int nparts = 1 << log2_parts;
     const u64 cap = 1ull << t.log2_cap;
     const u64 tile = (u64)kThreads * kExportItems;
@@ -286,17 +297,51 @@ __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, i
         __syncthreads();
         Tuple r[kExportItems];
         u32 rank[kExportItems];
+        u32 n_used = 0, pmin = 0xFFFFFFFFu, pmax = 0;
 #pragma unroll
         for (int k = 0; k < kExportItems; k++) {
             u64 s = tile0 + (u64)k * kThreads + threadIdx.x;
             r[k].used = false;
             if (s < cap) r[k] = read_slot<KLASS>(t, s, log2_parts);
-            if (r[k].used) rank[k] = atomicAdd(&cnt[r[k].part], 1u);
+            if (r[k].used) { n_used++; pmin = min(pmin, r[k].part); pmax = max(pmax, r[k].part); }
         }
-        __syncthreads();
-        for (int p = threadIdx.x; p < nparts; p += kThreads)
-            base[p] = cnt[p] ? atomicAdd(&cursors[p], (u64)cnt[p]) : 0;   // cursors start at the partition bases
-        __syncthreads();
+        // The table is hash-ordered: almost every tile lies inside ONE partition.  Then ranks come from a block scan of
+        // the per-thread counts; only a tile straddling a partition boundary ranks with shared-memory atomics.
+        const bool uniform = __syncthreads_and(n_used == 0 || pmin == pmax) != 0;
+        bool one_part = false;
+        if (uniform) {
+            // all threads that hold entries agree with their own pmin; agree across threads via shared memory
+            if (threadIdx.x == 0) { s_part[0] = 0xFFFFFFFFu; s_part[1] = 0; }
+            __syncthreads();
+            if (n_used) { atomicMin(&s_part[0], pmin); atomicMax(&s_part[1], pmin); }
+            __syncthreads();
+            one_part = s_part[0] == 0xFFFFFFFFu || s_part[0] == s_part[1];
+        }
+        if (one_part) {
+            // exclusive scan of n_used over the block
+            const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            u32 incl = n_used;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            u32 before = 0, total = 0;
+            for (int w = 0; w < kThreads / 32; w++) { if (w < (int)warp) before += s_warp[w]; total += s_warp[w]; }
+            if (threadIdx.x == 0) base[0] = total ? atomicAdd(&cursors[s_part[0]], (u64)total) : 0;
+            __syncthreads();
+            u32 run = before + incl - n_used;
+#pragma unroll
+            for (int k = 0; k < kExportItems; k++)
+                if (r[k].used) { rank[k] = run++; r[k].part = 0; }      // base[0] holds this tile's start
+        } else {
+#pragma unroll
+            for (int k = 0; k < kExportItems; k++)
+                if (r[k].used) rank[k] = atomicAdd(&cnt[r[k].part], 1u);
+            __syncthreads();
+            for (int p = threadIdx.x; p < nparts; p += kThreads)
+                base[p] = cnt[p] ? atomicAdd(&cursors[p], (u64)cnt[p]) : 0;   // cursors start at the partition bases
+            __syncthreads();
+        }
 #pragma unroll
         for (int k = 0; k < kExportItems; k++) {
             if (!r[k].used) continue;
