@@ -23,16 +23,14 @@
 //                 shared-memory cursor bump and an 8-byte store, no global atomics -- so that
 //                 ssq_counter.cu can insert partition by partition with the table region
 //                 resident in L2.
+#include <stdlib.h>
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
 
 namespace ssq {
 
 constexpr int kPackThreads = 256;
-#ifndef SSQ_RPT
-#define SSQ_RPT 2
-#endif
-constexpr int kRPT = SSQ_RPT;                         // reads per thread per tile (fixed classes)
+constexpr int kRPT = 2;                               // reads per thread per tile (fixed classes)
 constexpr int kTileReads = kPackThreads * kRPT;
 constexpr int kLoadUnroll = 4;                        // 16-byte loads in flight per thread
 
@@ -181,11 +179,10 @@ __device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets,
 // ---- ShortSeq64 / ShortSeq192 ------------------------------------------------------------------
 // Persistent CTAs walk the tiles with a grid stride.  The loop is software-pipelined: while a tile is being
 // extracted, the 16-byte loads of the CTA's next tile and the offsets of the one after are already in flight.
-#ifndef SSQ_MINB
-#define SSQ_MINB 1
-#endif
+// Three resident CTAs per SM (<= 85 registers) measured best on B200: two lose latency hiding, four (<= 64
+// registers) spill the prefetch state.
 template <int KLASS, int MODE>
-__global__ void __launch_bounds__(kPackThreads, SSQ_MINB) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+__global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     constexpr int MAXLEN = KLASS == SSQ_CLASS_64 ? 32 : 96;
     constexpr int MINLEN = KLASS == SSQ_CLASS_64 ? 0 : 33;
     constexpr int W = KLASS == SSQ_CLASS_64 ? 1 : 3;

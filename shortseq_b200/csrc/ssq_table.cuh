@@ -32,10 +32,7 @@ constexpr int kParts = 256;
 // in shared memory (one shared-memory atomicAdd each) and leave the SM only as whole, aligned 32-byte sectors
 // (4 keys, written with two 16-byte stores by the thread that owns the partition): isolated 8-byte stores to
 // 256 different places cost one memory transaction each, ~4x the time of this scheme (scripts/bench_scatter.cu).
-#ifndef SSQ_STAGECAP
-#define SSQ_STAGECAP 12
-#endif
-constexpr int kStageCap = SSQ_STAGECAP;   // staging slots per partition per CTA
+constexpr int kStageCap = 12;        // staging slots per partition per CTA
 struct PartView {
     u64 *keys;          // [num_ctas][kParts][seg_cap] table keys (key64_of) awaiting insertion
     u32 *seg_count;     // [num_ctas][kParts] entries per segment (written when the scatter CTA finishes)
