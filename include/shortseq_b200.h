@@ -175,9 +175,12 @@ int ssq_counter_lookup(ssq_counter *c, const uint64_t *words, const uint8_t *len
 int ssq_counter_size(ssq_counter *c, int64_t *n_unique);
 int ssq_counter_capacity(ssq_counter *c, int64_t *slots);
 /* Device time (CUDA events on the context's stream) of the last single-pass ssq_counter_pack_count:
- * phase 1 = fused pack (+ scatter to hash partitions for tables larger than L2), phase 2 = partition-ordered
- * insertion (0 when the keys were inserted directly).  For profiling. */
+ * phase 1 = fused pack (+ scatter to hash partitions for tables larger than L2), phase 2 = routing the keys to
+ * their table regions and counting them there (0 when the keys were inserted directly).  For profiling. */
 int ssq_counter_last_pass_ms(ssq_counter *c, float *phase1_ms, float *phase2_ms);
+/* The same pass split three ways: fused pack + level-1 scatter, level-2 (per table region) scatter, and the
+ * shared-memory region count.  The last two are 0 / everything-after-phase-1 when the keys took another path. */
+int ssq_counter_last_pass_detail(ssq_counter *c, float *pack_scatter_ms, float *region_scatter_ms, float *count_ms);
 /* Export all (key, len, count[, first_idx]) tuples, grouped into n_parts hash partitions
  * (owner = top log2(n_parts) bits of the key hash; n_parts a power of two, 1 = no
  * grouping).  Buffers must hold ssq_counter_size() tuples; part_counts[n_parts] (device)

@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C, time, sys, torch
 import shortseq_b200 as sq
 from shortseq_b200 import _lib

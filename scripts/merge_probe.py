@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Times the pieces of the multi-GPU merge on one GPU: export grouped by owner, weighted merge of one owner's share."""
 import sys, time, torch
 import shortseq_b200 as sq

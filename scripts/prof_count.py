@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Runs the fused pack+count a few times (for ncu captures)."""
 import sys
 import torch

@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Runs each kernel a few times at a mid size (for ncu captures: -k regex:<name> -s 1 -c 1)."""
 import sys
 import torch

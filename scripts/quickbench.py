@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Quick device timing of the main kernels (development aid, not the bench contract)."""
 import ctypes as C
 import sys
@@ -56,7 +57,10 @@ def main():
     bytes_pc = bytes_pack + nu * (8 * W + 9)
     p1, p2 = C.c_float(), C.c_float()
     lib.ssq_counter_last_pass_ms(ctr.handle, C.byref(p1), C.byref(p2))
-    print(f"pack+count:  {ms:8.3f} ms  {n*L/ms/1e6:8.1f} Gbases/s  {bytes_pc/ms/1e6:8.1f} GB/s algorithmic  uniques={nu}  phase1={p1.value:.3f} ms phase2={p2.value:.3f} ms")
+    d = [C.c_float(), C.c_float(), C.c_float()]
+    lib.ssq_counter_last_pass_detail(ctr.handle, C.byref(d[0]), C.byref(d[1]), C.byref(d[2]))
+    print(f"pack+count:  {ms:8.3f} ms  {n*L/ms/1e6:8.1f} Gbases/s  {bytes_pc/ms/1e6:8.1f} GB/s algorithmic  uniques={nu}  phase1={p1.value:.3f} ms phase2={p2.value:.3f} ms"
+          f"  (pack+scatter {d[0].value:.3f}, region scatter {d[1].value:.3f}, region count {d[2].value:.3f})")
     rep = ctx.sync()
     print("report", rep.code, rep.first_bad_read)
     arr = sq.ShortSeqArray(ctx, klass, words, lens)

@@ -17,6 +17,7 @@
 //     region stays resident in L2 -- random DRAM sector traffic becomes two streaming passes over
 //     8 bytes per read.  After the pass the table grows (x2) once it is more than 60 % full; a bound
 //     exceeded so badly that probing fails is reported as SSQ_ERR_TABLE_FULL, never silently.
+#include <stdlib.h>
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
 
@@ -40,7 +41,7 @@ __device__ __forceinline__ void block_add_new(const TableView &t, u32 my_new, u3
     __syncthreads();
     if (threadIdx.x == 0) {
         u64 tot = 0;
-        for (int k = 0; k < kThreads / 32; k++) tot += s_new[k];
+        for (int k = 0; k < (int)(blockDim.x / 32); k++) tot += s_new[k];
         if (tot) atomicAdd(t.size, tot);
     }
 }
@@ -133,20 +134,29 @@ __global__ void __launch_bounds__(kThreads) rehash_kernel(TableView src, TableVi
 }
 
 // ---- deferred (hash-partitioned) inserts, ShortSeq64 ------------------------------------------
+// Three streaming passes replace one random DRAM access per read:
+//   1. level-1 scatter (fused into the pack kernel, or scatter_packed_kernel for packed input): every key goes
+//      to one of 256 partitions (top 8 hash bits);
+//   2. region_scatter_kernel: the keys of one level-1 partition go on to the <= 256 table regions inside it;
+//   3. count_regions_kernel: one CTA per region loads the region's slots into shared memory, counts the
+//      region's keys with shared-memory atomics and writes the slots back -- the table itself is read and
+//      written exactly once, coalesced, and no global atomic is issued.
+// Tables whose regions do not fit in shared memory (>= 2^30 slots) fall back to count_parts_kernel, which inserts
+// level-1 partitions in order so that the table range being hit (cap/256 slots) stays resident in L2.
 constexpr int kCountKeysPerThread = 8;
+constexpr int kScatterRounds = 4;    // keys per thread between flushes
 
-// Phase 1 for already packed input: persistent CTAs stage their keys per hash partition and write whole
-// sectors to their own segments (see ssq_table.cuh).
-constexpr int kScatterRounds = 2;    // keys per thread between flushes
-__global__ void __launch_bounds__(kThreads) scatter_packed_kernel(TableView t, PartView pv, const u64 *words,
-                                                                  const uint8_t *lens, int64_t n, int64_t index_base) {
-    __shared__ __align__(16) u64 stage[kParts * kStageCap];
-    __shared__ u32 scnt[kParts];
-    __shared__ u32 sgcur[kParts];
+// Level 1 for already packed input.
+__global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t, PartView pv, const u64 *words,
+                                                                     const uint8_t *lens, int64_t n, int64_t index_base) {
+    extern __shared__ __align__(16) u64 dyn_ring[];
+    __shared__ u32 s_head[kParts], s_tail[kParts];
     __shared__ u32 s_new[kThreads / 32];
-    static_assert(kThreads == kParts, "thread p owns partition p's staging");
-    scnt[threadIdx.x] = 0;
-    sgcur[threadIdx.x] = 0;
+    __shared__ u32 s_unstaged_new;
+    const Stager stg{dyn_ring, s_head, s_tail};
+    u64 *const seg0 = pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap;
+    stager_init(stg);
+    if (threadIdx.x == 0) s_unstaged_new = 0;
     __syncthreads();
     u32 my_new = 0;
     const int64_t tile_keys = (int64_t)kThreads * kScatterRounds;
@@ -169,24 +179,189 @@ __global__ void __launch_bounds__(kThreads) scatter_packed_kernel(TableView t, P
             }
             const u64 h2 = rotl64(mix64(word[k]), t.rot);
             const u64 key = key64_of(h2, len[k]);
-            if (!stage_key(stage, scnt, (u32)(h2 >> 56), key)) {
+            if (!stage_key(stg, (u32)(h2 >> 56), key)) {
                 bool is_new = false;
                 insert64_hashed(t, h2, key, 1ull, is_new);
                 my_new += is_new ? 1u : 0u;
             }
         }
         __syncthreads();
-        flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, false, my_new);
+        flush_lines<false>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
         __syncthreads();
     }
-    flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, true, my_new);
-    pv.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = sgcur[threadIdx.x];
+    flush_lines<true>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+    __syncthreads();
+    pv.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = stager_seg_count(stg, threadIdx.x, pv.seg_cap);
+    if (threadIdx.x == 0) my_new += s_unstaged_new;
     block_add_new(t, my_new, s_new);
 }
 
-// Phase 2: insert the partitions in order.  Block b handles the segment that scatter CTA (b % num_ctas)
-// filled for partition (b / num_ctas); blocks are scheduled in index order, so at any time the whole GPU
-// works on one or two neighbouring partitions whose table region (cap/256 slots) stays in L2.
+// A CTA's input of the level-2 scatter / the region count: a few segments read as one concatenated stream.
+// pre[k] = number of keys in the segments before segment k (pre[nseg] = total); each thread walks the
+// segments monotonically, so the segment of an index is found by advancing a private cursor.
+constexpr int kMaxStreamSegs = 512;
+
+// Level 2: CTA (p, s) reads slice s of the level-1 segments of partition p (scatter CTAs [c0, c1)) and appends
+// every key to the segment of its level-2 partition (hash bits 55..48).
+__global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp) {
+    extern __shared__ __align__(16) u64 dyn_ring[];
+    __shared__ u32 s_head[kParts], s_tail[kParts];
+    __shared__ u32 pre[kMaxStreamSegs + 1];
+    __shared__ u32 s_unstaged_new;
+    const Stager stg{dyn_ring, s_head, s_tail};
+    const u32 p = blockIdx.x / rp.slices, s = blockIdx.x - p * rp.slices;
+    const u32 c0 = (u32)((u64)pv.num_ctas * s / rp.slices), c1 = (u32)((u64)pv.num_ctas * (s + 1) / rp.slices);
+    const u32 nseg = c1 - c0;
+    u64 *const seg0 = rp.keys + (size_t)blockIdx.x * kParts * rp.seg_cap;
+    stager_init(stg);
+    if (threadIdx.x == 0) {
+        s_unstaged_new = 0;
+        u32 run = 0;
+        for (u32 k = 0; k < nseg; k++) { pre[k] = run; run += pv.seg_count[(size_t)(c0 + k) * kParts + p]; }
+        pre[nseg] = run;
+    }
+    __syncthreads();
+    const u32 total = pre[nseg];
+    u32 seg = 0;
+    for (u32 i0 = 0; i0 < total; i0 += kThreads * kScatterRounds) {
+        u64 k[kScatterRounds];
+#pragma unroll
+        for (int j = 0; j < kScatterRounds; j++) {
+            const u32 i = i0 + j * kThreads + threadIdx.x;
+            k[j] = 0;
+            if (i < total) {
+                while (i >= pre[seg + 1]) ++seg;
+                k[j] = pv.keys[((size_t)(c0 + seg) * kParts + p) * pv.seg_cap + (i - pre[seg])];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kScatterRounds; j++) {
+            if (k[j] == 0) continue;
+            if (!stage_key(stg, (u32)(k[j] >> 48) & 0xFFu, k[j])) insert_unstaged(t, k[j], p, &s_unstaged_new);
+        }
+        __syncthreads();
+        flush_lines<false>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
+        __syncthreads();
+    }
+    flush_lines<true>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
+    __syncthreads();
+    rp.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = stager_seg_count(stg, threadIdx.x, rp.seg_cap);
+    if (threadIdx.x == 0 && s_unstaged_new) atomicAdd(t.size, (u64)s_unstaged_new);
+}
+
+// Level 3: one CTA per table region.  Dynamic shared memory: keys u64[R] | deltas u32[R] | staging u64[KPT][threads]
+// (R = 2^log2_region slots).  The region's keys are loaded into shared memory; every warp then walks its share of
+// the region's key stream: a chunk of 32 x KPT keys is loaded coalesced (the next chunk is in flight meanwhile),
+// parked in per-thread staging slots, and consumed by a rolled loop in which every lane makes ONE probe of its
+// current key per iteration and fetches its next key when done -- lanes never wait for each other's probe
+// sequences, only for the warp's slowest lane per chunk.  Counts are accumulated as 32-bit deltas; at the end the
+// touched slots are written back (old count re-read from L2, where the region load asked it to stay).
+constexpr int kCountThreads = 256;
+constexpr int kCountKPT = 8;
+constexpr int kCountChunk = 32 * kCountKPT;
+
+static size_t count_regions_smem(int log2_region) {
+    return ((size_t)12 << log2_region) + sizeof(u64) * kCountKPT * kCountThreads;
+}
+
+__global__ void __launch_bounds__(kCountThreads, 3) count_regions_kernel(TableView t, RegionParts rp) {
+    extern __shared__ __align__(16) u64 dyn_region[];
+    __shared__ u32 pre[kMaxStreamSegs + 1];
+    __shared__ u32 s_new[kCountThreads / 32];
+    const u32 R = 1u << t.log2_region, rmask = R - 1;
+    u64 *ks = dyn_region;
+    u32 *ds = reinterpret_cast<u32 *>(dyn_region + R);
+    u64 *sk = dyn_region + R + R / 2 + threadIdx.x;          // this thread's staging slots: sk[r * kCountThreads]
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 region = blockIdx.x;
+    const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
+    const u32 p = region >> rp.qbits, q = region & ((1u << rp.qbits) - 1);
+    const u32 nseg = rp.slices << sub_bits;                   // stream segment k = (slice k >> sub_bits, level-2 partition (q << sub_bits) | (k & sub_mask))
+    auto seg_index = [&](u32 k) -> size_t { return ((size_t)p * rp.slices + (k >> sub_bits)) * kParts + ((q << sub_bits) | (k & sub_mask)); };
+    if (warp == 0) {                                          // pre[] = exclusive scan of the segment sizes
+        u32 carry = 0;
+        for (u32 b = 0; b < nseg; b += 32) {
+            const u32 k = b + lane;
+            const u32 v = k < nseg ? rp.seg_count[seg_index(k)] : 0u;
+            u32 incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+            if (k < nseg) pre[k + 1] = carry + incl;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) pre[0] = 0;
+    }
+    const u64 keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
+    for (u32 i = threadIdx.x; i < R; i += kCountThreads) {
+        ks[i] = ld_hint_v2u64(gslots + i, keep).x;
+        ds[i] = 0;
+    }
+    __syncthreads();
+    const u32 total = pre[nseg];
+    const int off_shift = 64 - t.log2_cap;      // home slot = h2 >> off_shift; its low log2_region bits lie inside the key's hash bits
+    u32 my_new = 0, overflow = 0, seg = 0;
+    u64 nk[kCountKPT];
+    auto load_chunk = [&](u32 c) {
+#pragma unroll
+        for (int r = 0; r < kCountKPT; r++) {
+            const u32 i = c * kCountChunk + r * 32 + lane;
+            nk[r] = 0;
+            if (i < total) {
+                while (i >= pre[seg + 1]) ++seg;
+                nk[r] = ld_stream_u64(rp.keys + seg_index(seg) * rp.seg_cap + (i - pre[seg]), drop);
+            }
+        }
+    };
+    u32 c = warp;
+    if (c * kCountChunk < total) load_chunk(c);
+    while (c * kCountChunk < total) {
+#pragma unroll
+        for (int r = 0; r < kCountKPT; r++) sk[r * kCountThreads] = nk[r];
+        c += kCountThreads / 32;
+        if (c * kCountChunk < total) load_chunk(c);          // in flight while this chunk is counted
+        u32 r = 0, off = 0, left = 0;
+        u64 key = 0;                                          // 0 = this lane is between keys
+        for (;;) {
+            if (key == 0 && r < (u32)kCountKPT) {
+                key = sk[r * kCountThreads];
+                ++r;
+                off = (u32)(key >> off_shift) & rmask;
+                left = R;
+            }
+            if (!__any_sync(0xFFFFFFFFu, key != 0 || r < (u32)kCountKPT)) break;
+            if (key != 0) {
+                u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
+                if (cur == 0) {
+                    cur = atomicCAS(ks + off, 0ull, key);
+                    if (cur == 0) { ++my_new; cur = key; }
+                }
+                if (cur == key) {
+                    atomicAdd(ds + off, 1u);
+                    key = 0;
+                } else {
+                    off = (off + 1) & rmask;
+                    if (--left == 0) { ++overflow; key = 0; }          // the region is full
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < R; i += kCountThreads) {
+        const u32 d = ds[i];
+        if (d) {
+            const ulonglong2 old = gslots[i];
+            gslots[i] = make_ulonglong2(ks[i], old.y + d);
+        }
+    }
+    if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
+    block_add_new(t, my_new, s_new);
+}
+
+// Fallback for tables whose regions exceed shared memory: insert the level-1 partitions in order.  Block b handles
+// the segment that scatter CTA (b % num_ctas) filled for partition (b / num_ctas); blocks are scheduled in index
+// order, so at any time the whole GPU works on one or two neighbouring partitions whose table range (cap/256
+// slots) stays in L2.
 __global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, PartView pv) {
     __shared__ u32 s_new[kThreads / 32];
     const u32 p = blockIdx.x / pv.num_ctas;
@@ -370,6 +545,7 @@ static TableView view_of(const ssq_counter *c) {
     t.rep = c->ctx->d_report;
     t.log2_cap = c->log2_cap;
     t.rot = c->hash_rot;
+    t.log2_region = region_bits_for(c->log2_cap);
     return t;
 }
 
@@ -397,6 +573,7 @@ static int grow(ssq_counter *c, int new_log2) {
     dst.slots = (u64 *)nslots_p;
     dst.first_idx = nfirst;
     dst.log2_cap = new_log2;
+    dst.log2_region = region_bits_for(new_log2);
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), st));
     int grid = grid_for(ctx, ((int64_t)1 << c->log2_cap) / kThreads, 8);
     if (c->klass == SSQ_CLASS_64) rehash_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, st>>>(src, dst);
@@ -456,13 +633,13 @@ static bool use_deferred(const ssq_counter *c, int64_t n) {
 
 int scatter_grid(ssq_ctx *ctx, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
 
-// Size the partition buffers for a pass of n keys scattered by `grid` persistent CTAs.
+// Size the level-1 partition buffers for a pass of n keys scattered by `grid` persistent CTAs.
 static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     ssq_ctx *ctx = c->ctx;
     // a CTA sees ~n/grid keys, 1/256 of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
     int64_t per = n / ((int64_t)grid * kParts);
     per = per + per / 16 + 64;
-    per = (per + 3) & ~(int64_t)3;
+    per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
     const int64_t need = per * grid * kParts;
     if (need > c->part_cap) {
         SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -487,8 +664,88 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     return SSQ_OK;
 }
 
-static int launch_count_parts(ssq_counter *c, const PartView &pv) {
-    count_parts_kernel<<<kParts * pv.num_ctas, kThreads, 0, c->ctx->stream>>>(view_of(c), pv);
+// Regions of up to 2^13 slots (128 KB) are counted in shared memory.
+static bool regions_fit_smem(const ssq_counter *c) {
+    const int lr = region_bits_for(c->log2_cap);
+    return c->log2_cap >= 22 && lr <= 13;       // >= 2^22 slots: at most 64 level-2 partitions per region
+}
+
+static int region_slices() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("SSQ_REGION_SLICES");
+        v = e ? atoi(e) : 6;
+        if (v < 1) v = 1;
+        if (v > kMaxStreamSegs) v = kMaxStreamSegs;
+    }
+    return v;
+}
+
+// Size the level-2 (per region) buffers for n keys.
+static int prepare_regions(ssq_counter *c, int64_t n, RegionParts *rp) {
+    ssq_ctx *ctx = c->ctx;
+    const int lr = region_bits_for(c->log2_cap);
+    const int qbits = c->log2_cap - 8 - lr;
+    const int slices = region_slices();
+    if ((slices << (8 - qbits)) > kMaxStreamSegs) { set_error("too many level-2 segments per region"); return SSQ_ERR_ARG; }
+    int64_t per = n / ((int64_t)kParts * slices * kParts);
+    per = per + per / 16 + 64;
+    per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
+    const int64_t nseg = (int64_t)kParts * slices * kParts;
+    const int64_t need = per * nseg;
+    if (need > c->region_cap) {
+        SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (c->region_keys) SSQ_CUDA(cudaFree(c->region_keys));
+        c->region_keys = nullptr;
+        c->region_cap = 0;
+        SSQ_CUDA(cudaMalloc(&c->region_keys, sizeof(u64) * (size_t)need));
+        c->region_cap = need;
+    }
+    if (nseg > c->region_segs) {
+        SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (c->region_cursor) SSQ_CUDA(cudaFree(c->region_cursor));
+        c->region_cursor = nullptr;
+        c->region_segs = 0;
+        SSQ_CUDA(cudaMalloc(&c->region_cursor, sizeof(u32) * (size_t)nseg));
+        c->region_segs = nseg;
+    }
+    rp->keys = c->region_keys;
+    rp->seg_count = c->region_cursor;
+    rp->seg_cap = (u32)per;
+    rp->slices = (u32)slices;
+    rp->qbits = (u32)qbits;
+    return SSQ_OK;
+}
+
+static int set_max_smem(const void *kernel, size_t bytes) {
+    SSQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    SSQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return SSQ_OK;
+}
+
+// Phase 2 of the deferred path: count the keys of the level-1 partitions `pv` into the table.
+// ev_mid (may be null) is recorded between the level-2 scatter and the region count.
+static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cudaEvent_t ev_mid) {
+    ssq_ctx *ctx = c->ctx;
+    const TableView t = view_of(c);
+    if (!regions_fit_smem(c) || pv.num_ctas > (u32)kMaxStreamSegs) {
+        if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
+        count_parts_kernel<<<kParts * pv.num_ctas, kThreads, 0, ctx->stream>>>(t, pv);
+        SSQ_LAUNCH_CHECK();
+        return SSQ_OK;
+    }
+    RegionParts rp;
+    int rc = prepare_regions(c, n, &rp);
+    if (rc) return rc;
+    rc = set_max_smem((const void *)region_scatter_kernel, kStagerRingBytes);
+    if (rc) return rc;
+    region_scatter_kernel<<<kParts * rp.slices, kThreads, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+    SSQ_LAUNCH_CHECK();
+    if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
+    const size_t region_bytes = count_regions_smem(t.log2_region);
+    rc = set_max_smem((const void *)count_regions_kernel, region_bytes);
+    if (rc) return rc;
+    count_regions_kernel<<<1u << (t.log2_cap - t.log2_region), kCountThreads, region_bytes, ctx->stream>>>(t, rp);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -526,15 +783,16 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
         rc = launch_pack_count(ctx, c->klass, true, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c), pv, nullptr);
         if (rc) return rc;
         SSQ_CUDA(cudaEventRecord(c->ev[1], ctx->stream));
-        rc = launch_count_parts(c, pv);
+        rc = launch_count_parts(c, n, pv, c->ev[2]);
     } else {
         c->last_pass_phases = 1;
         rc = launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c),
                                PartView{}, nullptr);
         SSQ_CUDA(cudaEventRecord(c->ev[1], ctx->stream));
+        SSQ_CUDA(cudaEventRecord(c->ev[2], ctx->stream));
     }
     if (rc) return rc;
-    SSQ_CUDA(cudaEventRecord(c->ev[2], ctx->stream));
+    SSQ_CUDA(cudaEventRecord(c->ev[3], ctx->stream));
     return finish_pass(c);
 }
 
@@ -563,8 +821,12 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->part_cursor = nullptr;
     c->part_cap = 0;
     c->part_ctas = 0;
+    c->region_keys = nullptr;
+    c->region_cursor = nullptr;
+    c->region_cap = 0;
+    c->region_segs = 0;
     c->last_pass_phases = 0;
-    for (int i = 0; i < 3; i++) SSQ_CUDA(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 4; i++) SSQ_CUDA(cudaEventCreate(&c->ev[i]));
     const size_t bytes = ((size_t)1 << c->log2_cap) * slot_bytes(klass);
     SSQ_CUDA(cudaMalloc(&c->slots, bytes));
     SSQ_CUDA(cudaMalloc(&c->d_size, 4 * sizeof(u64)));
@@ -585,7 +847,9 @@ int ssq_counter_destroy(ssq_counter *c) {
     cudaFree(c->first_idx);
     cudaFree(c->part_keys);
     cudaFree(c->part_cursor);
-    for (int i = 0; i < 3; i++) cudaEventDestroy(c->ev[i]);
+    cudaFree(c->region_keys);
+    cudaFree(c->region_cursor);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_size);
     cudaFreeHost(c->h_size);
     delete c;
@@ -613,12 +877,14 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
         int rc = SSQ_OK;
         if (counts == nullptr && use_deferred(c, n)) {
             PartView pv;
-            int grid = grid_for(ctx, (n + 65535) / 65536, 8);
+            int grid = grid_for(ctx, (n + 65535) / 65536, 3);
             rc = prepare_parts(c, n, grid, &pv);
             if (rc) return rc;
-            scatter_packed_kernel<<<grid, kThreads, 0, ctx->stream>>>(view_of(c), pv, (const u64 *)words, lens, n, 0);
+            rc = set_max_smem((const void *)scatter_packed_kernel, kStagerRingBytes);
+            if (rc) return rc;
+            scatter_packed_kernel<<<grid, kThreads, kStagerRingBytes, ctx->stream>>>(view_of(c), pv, (const u64 *)words, lens, n, 0);
             SSQ_LAUNCH_CHECK();
-            rc = launch_count_parts(c, pv);
+            rc = launch_count_parts(c, n, pv, nullptr);
         } else {
             int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
             if (c->klass == SSQ_CLASS_64)
@@ -716,9 +982,21 @@ int ssq_counter_last_pass_ms(ssq_counter *c, float *phase1_ms, float *phase2_ms)
     *phase1_ms = *phase2_ms = 0.0f;
     if (c->last_pass_phases == 0) return SSQ_OK;
     DeviceGuard g(c->ctx->device);
-    SSQ_CUDA(cudaEventSynchronize(c->ev[2]));
+    SSQ_CUDA(cudaEventSynchronize(c->ev[3]));
     SSQ_CUDA(cudaEventElapsedTime(phase1_ms, c->ev[0], c->ev[1]));
-    SSQ_CUDA(cudaEventElapsedTime(phase2_ms, c->ev[1], c->ev[2]));
+    SSQ_CUDA(cudaEventElapsedTime(phase2_ms, c->ev[1], c->ev[3]));
+    return SSQ_OK;
+}
+
+int ssq_counter_last_pass_detail(ssq_counter *c, float *pack_scatter_ms, float *region_scatter_ms, float *count_ms) {
+    SSQ_ARG(c != nullptr && pack_scatter_ms != nullptr && region_scatter_ms != nullptr && count_ms != nullptr, "NULL argument");
+    *pack_scatter_ms = *region_scatter_ms = *count_ms = 0.0f;
+    if (c->last_pass_phases == 0) return SSQ_OK;
+    DeviceGuard g(c->ctx->device);
+    SSQ_CUDA(cudaEventSynchronize(c->ev[3]));
+    SSQ_CUDA(cudaEventElapsedTime(pack_scatter_ms, c->ev[0], c->ev[1]));
+    SSQ_CUDA(cudaEventElapsedTime(region_scatter_ms, c->ev[1], c->ev[2]));
+    SSQ_CUDA(cudaEventElapsedTime(count_ms, c->ev[2], c->ev[3]));
     return SSQ_OK;
 }
 

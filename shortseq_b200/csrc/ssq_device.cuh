@@ -54,6 +54,28 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// L2 cache policies: keep a line that will be touched again soon / drop a line that is read exactly once.
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_hint_v2u64(const void *p, u64 policy) {
+    ulonglong2 r;
+    asm volatile("ld.global.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy) : "memory");
+    return r;
+}
+// 8-byte streaming load: no L1 allocation, L2 line dropped first
+__device__ __forceinline__ u64 ld_stream_u64(const void *p, u64 policy) {
+    u64 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
+    return r;
+}
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

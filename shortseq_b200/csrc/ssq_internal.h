@@ -32,7 +32,11 @@ struct ssq_counter {
     ssq::u32 *part_cursor;     // [part_ctas][kParts] segment fill counts
     int64_t part_cap;          // key entries currently allocated
     int part_ctas;             // scatter CTAs the count array is sized for
-    cudaEvent_t ev[3];         // start / end of phase 1 / end of phase 2 of the last bounded pass
+    ssq::u64 *region_keys;     // level-2 (per table region) buffers of the deferred path
+    ssq::u32 *region_cursor;   // [kParts][slices][kParts] segment fill counts
+    int64_t region_cap;        // key entries currently allocated
+    int64_t region_segs;       // segments the count array is sized for
+    cudaEvent_t ev[4];         // last bounded pass: start / after pack+scatter / after the region scatter / end
     int last_pass_phases;      // 0 none, 1 direct single kernel, 2 deferred (scatter + count)
 };
 

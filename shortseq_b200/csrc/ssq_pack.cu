@@ -19,10 +19,10 @@
 // Counting modes of the fixed-class kernel:
 //   kModeDirect   insert each key straight into the table (tables that fit in L2),
 //   kModeScatter  append each key's 64-bit table key to one of 256 hash partitions -- every
-//                 persistent CTA owns a private segment of every partition, so the append is a
-//                 shared-memory cursor bump and an 8-byte store, no global atomics -- so that
-//                 ssq_counter.cu can insert partition by partition with the table region
-//                 resident in L2.
+//                 persistent CTA owns a private segment of every partition and stages keys in
+//                 shared-memory rings that are flushed as whole 128-byte lines, no global
+//                 atomics -- so that ssq_counter.cu can route the keys on to their table
+//                 region and count them in shared memory.
 #include <stdlib.h>
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
@@ -192,15 +192,19 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
     __shared__ u32 codes[MAX_CHUNKS + PAD];
     __shared__ u32 srel[kTileReads + 1];                // read starts relative to the tile start
     __shared__ u32 s_new[kPackThreads / 32];
-    // scatter mode: per-partition staging of this CTA (see ssq_table.cuh)
-    __shared__ __align__(16) u64 stage[MODE == kModeScatter ? kParts * kStageCap : 1];
-    __shared__ u32 scnt[MODE == kModeScatter ? kParts : 1];
-    __shared__ u32 sgcur[MODE == kModeScatter ? kParts : 1];
-    static_assert(kPackThreads == kParts, "thread p owns partition p's staging");
+    // scatter mode: per-partition staging rings of this CTA (see Stager in ssq_table.cuh) in dynamic shared memory
+    extern __shared__ __align__(16) u64 dyn_ring[];
+    __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 s_unstaged_new;
+    const Stager stg{dyn_ring, s_head, s_tail};
+    u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;
-    if (MODE == kModeScatter)
-        for (int p = threadIdx.x; p < kParts; p += kPackThreads) { scnt[p] = 0; sgcur[p] = 0; }   // ordered by the first tile's barrier
+    if (MODE == kModeScatter) {                      // ordered by the first tile's barrier
+        stager_init(stg);
+        if (threadIdx.x == 0) s_unstaged_new = 0;
+    }
 
     u32 my_new = 0;
     const int64_t ntiles = (a.n + kTileReads - 1) / kTileReads;
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
                         // stage the table key for its hash partition
                         const u64 h2 = rotl64(mix64(w[0]), t.rot);
                         const u64 key = key64_of(h2, (u32)len);
-                        if (!stage_key(stage, scnt, (u32)(h2 >> 56), key)) {   // staging full: count it right away
+                        if (!stage_key(stg, (u32)(h2 >> 56), key)) {   // staging ring full: count it right away
                             bool is_new = false;
                             insert64_hashed(t, h2, key, 1ull, is_new);
                             my_new += is_new ? 1u : 0u;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
             }
             if constexpr (MODE == kModeScatter) {
                 __syncthreads();
-                flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, false, my_new);
+                flush_lines<false>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
             }
         }
         __syncthreads();   // codes[] / srel[] are rewritten by the next tile
@@ -314,8 +318,11 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
         cur = nxt; cur_ok = nxt_ok; geom = ngeom; prefetched = nprefetched; nxt = nxt2;
     }
     if constexpr (MODE == kModeScatter) {
-        flush_staged(stage, scnt, sgcur, threadIdx.x, pv, t, true, my_new);   // the loop ended with a barrier
-        pv.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = sgcur[threadIdx.x];
+        flush_lines<true>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);   // the loop ended with a barrier
+        __syncthreads();
+        for (int p = threadIdx.x; p < kParts; p += kPackThreads)
+            pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
+        if (threadIdx.x == 0) my_new += s_unstaged_new;
     }
     if (MODE != kModePack) {
         // one size update per CTA: a single global counter cannot take one atomic per warp
@@ -387,11 +394,33 @@ __global__ void __launch_bounds__(kPackThreads) pack_var_kernel(PackArgs a) {
 }
 
 // Persistent grid: exactly as many CTAs as are resident at once (one wave), capped by the number of tiles.
+template <int MODE>
+constexpr size_t pack_dyn_smem() { return MODE == kModeScatter ? kStagerRingBytes : 0; }
+
+// The scatter mode needs 64 KB of dynamic shared memory per CTA (three CTAs per SM = most of the 227 KB).
+template <int KLASS, int MODE>
+static int prepare_fixed_kernel() {
+    if (MODE == kModeScatter) {
+        static bool done = false;      // per process; attributes are per device but identical on every B200
+        static int done_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!done || done_dev != dev) {
+            SSQ_CUDA(cudaFuncSetAttribute(pack_fixed_kernel<KLASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE>()));
+            SSQ_CUDA(cudaFuncSetAttribute(pack_fixed_kernel<KLASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            done = true;
+            done_dev = dev;
+        }
+    }
+    return SSQ_OK;
+}
+
 template <int KLASS, int MODE>
 static int fixed_grid(ssq_ctx *ctx, int64_t n) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_fixed_kernel<KLASS, MODE>, kPackThreads, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
+    if (prepare_fixed_kernel<KLASS, MODE>() != SSQ_OK) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_fixed_kernel<KLASS, MODE>, kPackThreads, pack_dyn_smem<MODE>()) != cudaSuccess || per_sm < 1)
+        per_sm = MODE == kModeScatter ? 3 : 4;
     return grid_for(ctx, (n + kTileReads - 1) / kTileReads, per_sm);
 }
 
@@ -399,7 +428,9 @@ template <int KLASS, int MODE>
 static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid = 0) {
     if (a.n <= 0) return SSQ_OK;
     if (grid <= 0) grid = fixed_grid<KLASS, MODE>(ctx, a.n);
-    pack_fixed_kernel<KLASS, MODE><<<grid, kPackThreads, 0, ctx->stream>>>(a, t, pv, stop);
+    int rc = prepare_fixed_kernel<KLASS, MODE>();
+    if (rc) return rc;
+    pack_fixed_kernel<KLASS, MODE><<<grid, kPackThreads, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

@@ -8,9 +8,12 @@
 //   home slot = top log2(cap) bits of h2 -> the table is ordered by hash, so a
 //               hash partition is a contiguous slot range (multi-GPU export,
 //               L2-sized insertion passes)
-//   key = low 56 bits of h2 | (len+1) << 56 | (bit 56 of h2) << 62
-//   The top 8 bits of h2 are not stored: with linear probing bounded to less than
-//   cap/256 slots they follow from the slot position and the stored parity bit.
+//   key = low 58 bits of h2 | (len+1) << 58
+//   The table is cut into REGIONS of 2^lr slots (lr = region_bits_for(log2 cap): 12 for tables of
+//   2^20..2^28 slots, so there are 256..65536 regions); linear probing wraps around inside the
+//   key's region.  The top 6 bits of h2 are therefore not stored: a region lies inside one 1/64 of
+//   the table, so they are the top 6 bits of the slot index.  A region is also the unit the deferred counting pass loads into shared memory
+//   (64 KB at lr = 12): keys are routed to their region by two 256-way scatters.
 //   len+1 >= 1 makes every key non-zero, so 0 marks an empty slot and one 64-bit
 //   atomicCAS claims a slot AND publishes the whole key.
 //
@@ -24,20 +27,33 @@
 namespace ssq {
 
 constexpr u64 kMask56 = (1ull << 56) - 1;
+constexpr u64 kMask58 = (1ull << 58) - 1;   // hash bits kept in a ShortSeq64 table key
 constexpr int kMinLog2Cap = 16;
 
-// Hash partitions of the deferred-insert path: partition = top 8 bits of h2, i.e. 1/256 of the slot range.
+// Hash partitions of the deferred-insert path.  Level 1: partition = top 8 bits of h2, i.e. 1/256 of the slot
+// range.  Level 2 (inside one level-1 partition): the next bits of h2 down to one table region.
+// Every CTA of a scatter pass owns a private segment of every partition, so appending needs no global atomics.
+// Isolated 8-byte stores to 256 different places cost one memory transaction each (scripts/bench_scatter.cu);
+// keys are therefore staged per partition in shared memory and written as whole 128-byte lines (see Stager).
 constexpr int kParts = 256;
-// Every CTA of the scatter pass owns a private segment of every partition.  Keys are first staged per partition
-// in shared memory (one shared-memory atomicAdd each) and leave the SM only as whole, aligned 32-byte sectors
-// (4 keys, written with two 16-byte stores by the thread that owns the partition): isolated 8-byte stores to
-// 256 different places cost one memory transaction each, ~4x the time of this scheme (scripts/bench_scatter.cu).
-constexpr int kStageCap = 12;        // staging slots per partition per CTA
+constexpr int kLineKeys = 16;        // keys per flushed line (128 bytes)
+constexpr int kRingKeys = 2 * kLineKeys;   // staging ring per partition per CTA
+constexpr size_t kStagerRingBytes = (size_t)kParts * kRingKeys * sizeof(u64);   // 64 KB of dynamic shared memory
 struct PartView {
     u64 *keys;          // [num_ctas][kParts][seg_cap] table keys (key64_of) awaiting insertion
     u32 *seg_count;     // [num_ctas][kParts] entries per segment (written when the scatter CTA finishes)
-    u32 seg_cap;        // entries per segment (multiple of 4); keys beyond it are inserted directly by the scatter pass
+    u32 seg_cap;        // entries per segment (multiple of kLineKeys); keys beyond it are inserted directly by the scatter pass
     u32 num_ctas;       // grid size of the scatter pass
+};
+// Level-2 buffers: CTA (p, s) of the second scatter -- slice s of level-1 partition p -- owns the segments
+// keys[((p * slices + s) * kParts + r) * seg_cap ...] of the level-2 partitions r (hash bits 55..48) of partition p.
+// A table region of partition p is 2^(8 - qbits) consecutive level-2 partitions (exactly one for 2^28 slots).
+struct RegionParts {
+    u64 *keys;
+    u32 *seg_count;     // [kParts][slices][kParts]
+    u32 seg_cap;
+    u32 slices;         // CTAs per level-1 partition
+    u32 qbits;          // log2(regions per level-1 partition) <= 8
 };
 
 struct TableView {
@@ -47,20 +63,29 @@ struct TableView {
     DevReport *rep;
     int log2_cap;
     int rot;
+    int log2_region;  // ShortSeq64 tables: probing wraps inside regions of 2^log2_region slots
 };
+
+// Regions of 2^12 slots for tables of 2^18 .. 2^28 slots (64 .. 65536 regions); 1/64 of a smaller table; larger
+// regions beyond 2^28 slots so that a level-1 partition never holds more than 256 of them.
+__host__ __device__ __forceinline__ int region_bits_for(int log2_cap) {
+    return log2_cap < 18 ? log2_cap - 6 : (log2_cap <= 28 ? 12 : log2_cap - 16);
+}
 
 // ---- ShortSeq64 ------------------------------------------------------------
 __device__ __forceinline__ u64 key64_of(u64 h2, u32 len) {
-    return (h2 & kMask56) | ((u64)(len + 1) << 56) | (((h2 >> 56) & 1ull) << 62);
+    return (h2 & kMask58) | ((u64)(len + 1) << 58);
 }
 
 // Returns the slot index (or kNoIndex on overflow); is_new is set when this call created the key.
 __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 key, u64 add, bool &is_new) {
-    const u64 mask = (1ull << t.log2_cap) - 1;
-    const u32 limit = 1u << (t.log2_cap - 8);
-    u64 slot = h2 >> (64 - t.log2_cap);
+    const u32 rmask = (1u << t.log2_region) - 1;
+    const u64 home = h2 >> (64 - t.log2_cap);
+    const u64 base = home & ~(u64)rmask;
+    u32 off = (u32)home & rmask;
     is_new = false;
-    for (u32 probe = 0; probe < limit; ++probe) {
+    for (u32 probe = 0; probe <= rmask; ++probe) {
+        const u64 slot = base | off;
         u64 *p = t.slots + 2 * slot;
         u64 k = ld_relaxed_u64(p);
         if (k == 0) {
@@ -68,9 +93,9 @@ __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 k
             if (k == 0) { red_add_u64(p + 1, add); is_new = true; return slot; }
         }
         if (k == key) { red_add_u64(p + 1, add); return slot; }
-        slot = (slot + 1) & mask;
+        off = (off + 1) & rmask;
     }
-    atomicAdd(&t.rep->table_overflow, 1ull);
+    atomicAdd(&t.rep->table_overflow, 1ull);   // the key's region is full
     return kNoIndex;
 }
 
@@ -80,26 +105,28 @@ __device__ __forceinline__ u64 insert64(const TableView &t, u64 word, u32 len, u
 }
 
 __device__ __forceinline__ u64 find64(const TableView &t, u64 word, u32 len) {
-    const u64 mask = (1ull << t.log2_cap) - 1;
-    const u32 limit = 1u << (t.log2_cap - 8);
+    const u32 rmask = (1u << t.log2_region) - 1;
     u64 h2 = rotl64(mix64(word), t.rot);
     u64 key = key64_of(h2, len);
-    u64 slot = h2 >> (64 - t.log2_cap);
-    for (u32 probe = 0; probe < limit; ++probe) {
+    const u64 home = h2 >> (64 - t.log2_cap);
+    const u64 base = home & ~(u64)rmask;
+    u32 off = (u32)home & rmask;
+    for (u32 probe = 0; probe <= rmask; ++probe) {
+        const u64 slot = base | off;
         u64 k = ld_relaxed_u64(t.slots + 2 * slot);
         if (k == key) return slot;
         if (k == 0) return kNoIndex;
-        slot = (slot + 1) & mask;
+        off = (off + 1) & rmask;
     }
     return kNoIndex;
 }
 
-// Recover (h2, len) of an occupied ShortSeq64 slot.
+// Recover (h2, len) of an occupied ShortSeq64 slot: probing never leaves the region, and a region lies inside
+// one 1/64 of the table, so the top 6 bits of h2 are the top 6 bits of the slot index.
 __device__ __forceinline__ u64 slot64_h2(const TableView &t, u64 slot, u64 key, u32 &len) {
-    u64 g = slot >> (t.log2_cap - 8);
-    if ((g & 1ull) != ((key >> 62) & 1ull)) g = (g - 1) & 0xFFull;
-    len = (u32)((key >> 56) & 0x3F) - 1;
-    return (g << 56) | (key & kMask56);
+    const u64 g = slot >> (t.log2_cap - 6);
+    len = (u32)(key >> 58) - 1;
+    return (g << 58) | (key & kMask58);
 }
 
 // ---- ShortSeq192 -----------------------------------------------------------
@@ -159,46 +186,95 @@ __device__ __forceinline__ u64 find192(const TableView &t, u64 w0, u64 w1, u64 w
 }
 
 // ---- staged scatter into hash partitions (ShortSeq64) ------------------------------------------
-// Append one table key to the CTA's staging area; returns false when the partition's staging is full (the
-// caller then inserts the key directly).
-__device__ __forceinline__ bool stage_key(u64 *stage, u32 *scnt, u32 part, u64 key) {
-    const u32 pos = atomicAdd(&scnt[part], 1u);
-    if (pos >= (u32)kStageCap) return false;
-    stage[part * kStageCap + pos] = key;
+// Shared-memory staging of one scatter CTA: a ring of kRingKeys keys per partition plus two monotonic
+// cursors (head = keys staged so far, tail = keys already flushed).  Keys leave the SM only as whole,
+// aligned LINES of kLineKeys keys (128 bytes), copied by kLineKeys/2 neighbouring lanes with one 16-byte
+// store each -- one full-line memory transaction per 16 keys instead of one per key.
+struct Stager {
+    u64 *ring;     // [kParts][kRingKeys]
+    u32 *head;     // [kParts]
+    u32 *tail;     // [kParts]
+};
+
+__device__ __forceinline__ void stager_init(const Stager &s) {
+    for (u32 p = threadIdx.x; p < (u32)kParts; p += blockDim.x) { s.head[p] = 0; s.tail[p] = 0; }
+}
+
+// Append one key to partition `part`.  Returns false when the ring is full (more than kRingKeys keys of one
+// partition between two flushes: heavily skewed input); the caller then inserts the key directly.
+__device__ __forceinline__ bool stage_key(const Stager &s, u32 part, u64 key) {
+    const u32 pos = atomicAdd(&s.head[part], 1u);
+    if (pos - s.tail[part] >= (u32)kRingKeys) return false;     // flush_lines clamps head back
+    s.ring[part * kRingKeys + (pos & (kRingKeys - 1))] = key;
     return true;
 }
 
-// Thread `p` moves partition p's staged keys to the CTA's segment in global memory: whole sectors only, the
-// remainder (< 4 keys) stays staged -- unless `final`, which empties the staging.  Call between two barriers.
-__device__ __forceinline__ void flush_staged(u64 *stage, u32 *scnt, u32 *sgcur, u32 p, const PartView &pv, const TableView &t,
-                                             bool final, u32 &my_new) {
-    const u32 c = min(scnt[p], (u32)kStageCap);
-    const u32 nfl = final ? c : (c & ~3u);
-    u64 *src = stage + p * kStageCap;
-    if (nfl) {
-        const u32 g = sgcur[p];
-        if (g + nfl <= pv.seg_cap) {
-            u64 *dst = pv.keys + ((size_t)blockIdx.x * kParts + p) * pv.seg_cap + g;
-            u32 j = 0;
-            for (; j + 4 <= nfl; j += 4) {
-                const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(src + j);
-                const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(src + j + 2);
-                *reinterpret_cast<ulonglong2 *>(dst + j) = a;
-                *reinterpret_cast<ulonglong2 *>(dst + j + 2) = b;
-            }
-            for (; j < nfl; j++) dst[j] = src[j];
-            sgcur[p] = g + nfl;
-        } else {                                   // segment full: count these keys right away
-            for (u32 j = 0; j < nfl; j++) {
-                bool is_new = false;
-                insert64_hashed(t, ((u64)p << 56) | (src[j] & kMask56), src[j], 1ull, is_new);
-                my_new += is_new ? 1u : 0u;
+// Keys that find no room in their segment are counted right away.  `fixed_top` >= 0: the top 8 hash bits of
+// every key of this CTA (second-level scatter); < 0: the partition index is the top 8 bits (first level).
+static __device__ __noinline__ void insert_unstaged(const TableView &t, u64 key, u32 top, u32 *my_new) {
+    bool is_new = false;
+    insert64_hashed(t, ((u64)top << 56) | (key & kMask56), key, 1ull, is_new);
+    if (is_new) atomicAdd(my_new, 1u);
+}
+
+// Move every complete line (FINAL: everything) of the staging rings to this CTA's segments:
+// partition q's segment starts at seg0 + q * seg_cap (seg_cap a multiple of kLineKeys).  All threads of the
+// CTA call this between two barriers.  s_new is a shared-memory counter of keys created by the overflow path.
+template <bool FINAL>
+__device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_cap, const TableView &t, int fixed_top,
+                                            u32 *s_new) {
+    constexpr u32 kLaneGroup = kLineKeys / 2;           // lanes that copy one line (16 bytes each)
+    constexpr u32 kGroups = 32 / kLaneGroup;            // lines per warp-wide store
+    const u32 lane = threadIdx.x & 31;
+    const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
+    for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)kParts; pbase += blockDim.x) {
+        const u32 p = pbase + lane;
+        const u32 tl = s.tail[p];
+        const u32 hd = min(s.head[p], tl + (u32)kRingKeys);
+        const u32 avail = hd - tl;
+        const u32 nl = avail / kLineKeys;               // 0, 1 or 2 complete lines
+#pragma unroll
+        for (u32 pass = 0; pass < 2; pass++) {
+            u32 m = __ballot_sync(0xFFFFFFFFu, nl > pass);
+            while (m) {
+                int bit = -1;
+#pragma unroll
+                for (u32 k = 0; k < kGroups; k++) {      // group k takes the k-th lowest ready partition
+                    const int b = __ffs(m) - 1;
+                    if (k == g) bit = b;
+                    m &= m - 1;
+                }
+                if (bit >= 0) {
+                    const u32 q = pbase + (u32)bit;
+                    const u32 tq = s.tail[q] + pass * kLineKeys;
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s.ring + q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub);
+                    if (tq + kLineKeys <= seg_cap) {
+                        *reinterpret_cast<ulonglong2 *>(seg0 + (size_t)q * seg_cap + tq + 2 * sub) = v;
+                    } else {                              // segment full
+                        const u32 top = fixed_top >= 0 ? (u32)fixed_top : q;
+                        insert_unstaged(t, v.x, top, s_new);
+                        insert_unstaged(t, v.y, top, s_new);
+                    }
+                }
             }
         }
-        for (u32 j = nfl; j < c; j++) src[j - nfl] = src[j];
+        __syncwarp();
+        u32 flushed = nl * kLineKeys;
+        if (FINAL) {                                      // the partial last line, key by key (once per CTA)
+            for (u32 j = flushed; j < avail; j++) {
+                const u64 key = s.ring[p * kRingKeys + ((tl + j) & (kRingKeys - 1))];
+                if (tl + avail <= seg_cap) seg0[(size_t)p * seg_cap + tl + j] = key;
+                else insert_unstaged(t, key, fixed_top >= 0 ? (u32)fixed_top : p, s_new);
+            }
+            flushed = avail;
+        }
+        s.tail[p] = tl + flushed;
+        s.head[p] = hd;
     }
-    scnt[p] = c - nfl;
 }
+
+// entries of partition p's segment that were written to global memory (call after the FINAL flush + barrier)
+__device__ __forceinline__ u32 stager_seg_count(const Stager &s, u32 p, u32 seg_cap) { return min(s.tail[p], seg_cap); }
 
 // Add the number of keys this warp created to the table's size counter with one atomic per warp.
 __device__ __forceinline__ void add_new_keys(const TableView &t, bool is_new) {
