@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t
 constexpr int kMaxStreamSegs = 512;
 
 // Level 2: CTA (p, s) reads slice s of the level-1 segments of partition p (scatter CTAs [c0, c1)) and appends
-// every key to the segment of its level-2 partition (hash bits 55..48).
+// every key to the segment of its level-2 partition (hash bits 55..48).  The loads of the next tile are in
+// flight while the current tile is staged and flushed.
 __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp) {
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[kParts], s_tail[kParts];
@@ -214,26 +215,45 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     const u32 nseg = c1 - c0;
     u64 *const seg0 = rp.keys + (size_t)blockIdx.x * kParts * rp.seg_cap;
     stager_init(stg);
-    if (threadIdx.x == 0) {
-        s_unstaged_new = 0;
-        u32 run = 0;
-        for (u32 k = 0; k < nseg; k++) { pre[k] = run; run += pv.seg_count[(size_t)(c0 + k) * kParts + p]; }
-        pre[nseg] = run;
+    if (threadIdx.x == 0) s_unstaged_new = 0;
+    if (threadIdx.x < 32) {                                   // pre[] = exclusive scan of the segment sizes
+        const u32 lane = threadIdx.x;
+        u32 carry = 0;
+        for (u32 b = 0; b < nseg; b += 32) {
+            const u32 k = b + lane;
+            const u32 v = k < nseg ? pv.seg_count[(size_t)(c0 + k) * kParts + p] : 0u;
+            u32 incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+            if (k < nseg) pre[k + 1] = carry + incl;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) pre[0] = 0;
     }
     __syncthreads();
     const u32 total = pre[nseg];
+    const u64 drop = l2_policy_evict_first();
+    const u64 *const part0 = pv.keys + ((size_t)c0 * kParts + p) * pv.seg_cap;     // segment k starts at part0 + k * seg_stride
+    const size_t seg_stride = (size_t)kParts * pv.seg_cap;
     u32 seg = 0;
-    for (u32 i0 = 0; i0 < total; i0 += kThreads * kScatterRounds) {
-        u64 k[kScatterRounds];
+    u64 nk[kScatterRounds];
+    auto load_tile = [&](u32 i0) {
 #pragma unroll
         for (int j = 0; j < kScatterRounds; j++) {
             const u32 i = i0 + j * kThreads + threadIdx.x;
-            k[j] = 0;
+            nk[j] = 0;
             if (i < total) {
                 while (i >= pre[seg + 1]) ++seg;
-                k[j] = pv.keys[((size_t)(c0 + seg) * kParts + p) * pv.seg_cap + (i - pre[seg])];
+                nk[j] = ld_stream_u64(part0 + seg * seg_stride + (i - pre[seg]), drop);
             }
         }
+    };
+    if (total) load_tile(0);
+    for (u32 i0 = 0; i0 < total; i0 += kThreads * kScatterRounds) {
+        u64 k[kScatterRounds];
+#pragma unroll
+        for (int j = 0; j < kScatterRounds; j++) k[j] = nk[j];
+        if (i0 + kThreads * kScatterRounds < total) load_tile(i0 + kThreads * kScatterRounds);
 #pragma unroll
         for (int j = 0; j < kScatterRounds; j++) {
             if (k[j] == 0) continue;
@@ -249,30 +269,34 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     if (threadIdx.x == 0 && s_unstaged_new) atomicAdd(t.size, (u64)s_unstaged_new);
 }
 
-// Level 3: one CTA per table region.  Dynamic shared memory: keys u64[R] | deltas u32[R] | staging u64[KPT][threads]
-// (R = 2^log2_region slots).  The region's keys are loaded into shared memory; every warp then walks its share of
-// the region's key stream: a chunk of 32 x KPT keys is loaded coalesced (the next chunk is in flight meanwhile),
-// parked in per-thread staging slots, and consumed by a rolled loop in which every lane makes ONE probe of its
-// current key per iteration and fetches its next key when done -- lanes never wait for each other's probe
-// sequences, only for the warp's slowest lane per chunk.  Counts are accumulated as 32-bit deltas; at the end the
-// touched slots are written back (old count re-read from L2, where the region load asked it to stay).
-constexpr int kCountThreads = 256;
+// Level 3: one CTA per table region.  Dynamic shared memory: keys u64[R] | deltas u32[R] | per-warp key queues
+// u64[warps][32 * KPT] (R = 2^log2_region slots).  The region's keys are loaded into shared memory; every warp then
+// walks its share of the region's key stream in chunks of 32 x KPT keys, loaded coalesced (the next chunk is in
+// flight meanwhile) and parked in the warp's queue.  A rolled loop consumes the queue: in every iteration each lane
+// makes ONE probe of its current key, and lanes that finished a key take the next queue entries (ballot-ranked, no
+// atomics) -- no lane waits for another lane's probe sequence, and the queue is refilled as soon as it runs dry.
+// Counts are accumulated as 32-bit deltas; at the end the touched slots are written back (old count re-read from
+// L2, where the region load asked it to stay).
 constexpr int kCountKPT = 8;
 constexpr int kCountChunk = 32 * kCountKPT;
 
+template <int THREADS>
 static size_t count_regions_smem(int log2_region) {
-    return ((size_t)12 << log2_region) + sizeof(u64) * kCountKPT * kCountThreads;
+    return ((size_t)12 << log2_region) + sizeof(u64) * kCountKPT * THREADS;
 }
 
-__global__ void __launch_bounds__(kCountThreads, 3) count_regions_kernel(TableView t, RegionParts rp) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3)
+count_regions_kernel(TableView t, RegionParts rp) {
     extern __shared__ __align__(16) u64 dyn_region[];
     __shared__ u32 pre[kMaxStreamSegs + 1];
-    __shared__ u32 s_new[kCountThreads / 32];
+    __shared__ u32 s_new[THREADS / 32];
+    constexpr u32 W = THREADS / 32;
     const u32 R = 1u << t.log2_region, rmask = R - 1;
     u64 *ks = dyn_region;
     u32 *ds = reinterpret_cast<u32 *>(dyn_region + R);
-    u64 *sk = dyn_region + R + R / 2 + threadIdx.x;          // this thread's staging slots: sk[r * kCountThreads]
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *wq = dyn_region + R + R / 2 + warp * kCountChunk;     // this warp's key queue
     const u32 region = blockIdx.x;
     const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
     const u32 p = region >> rp.qbits, q = region & ((1u << rp.qbits) - 1);
@@ -293,13 +317,14 @@ __global__ void __launch_bounds__(kCountThreads, 3) count_regions_kernel(TableVi
     }
     const u64 keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
-    for (u32 i = threadIdx.x; i < R; i += kCountThreads) {
+    for (u32 i = threadIdx.x; i < R; i += THREADS) {
         ks[i] = ld_hint_v2u64(gslots + i, keep).x;
         ds[i] = 0;
     }
     __syncthreads();
     const u32 total = pre[nseg];
     const int off_shift = 64 - t.log2_cap;      // home slot = h2 >> off_shift; its low log2_region bits lie inside the key's hash bits
+    const u32 lt_mask = (1u << lane) - 1;
     u32 my_new = 0, overflow = 0, seg = 0;
     u64 nk[kCountKPT];
     auto load_chunk = [&](u32 c) {
@@ -314,40 +339,52 @@ __global__ void __launch_bounds__(kCountThreads, 3) count_regions_kernel(TableVi
         }
     };
     u32 c = warp;
-    if (c * kCountChunk < total) load_chunk(c);
-    while (c * kCountChunk < total) {
+    bool more = c * kCountChunk < total;         // warp-uniform: nk[] holds a chunk that is not yet in the queue
+    if (more) load_chunk(c);
+    u32 qpos = kCountChunk;                      // warp-uniform: next unread queue entry (>= kCountChunk: queue empty)
+    u32 off = 0, left = 0;
+    u64 key = 0;                                 // 0 = this lane is between keys
+    for (;;) {
+        if (qpos >= (u32)kCountChunk && more) {  // refill the queue, start the loads of the chunk after it
 #pragma unroll
-        for (int r = 0; r < kCountKPT; r++) sk[r * kCountThreads] = nk[r];
-        c += kCountThreads / 32;
-        if (c * kCountChunk < total) load_chunk(c);          // in flight while this chunk is counted
-        u32 r = 0, off = 0, left = 0;
-        u64 key = 0;                                          // 0 = this lane is between keys
-        for (;;) {
-            if (key == 0 && r < (u32)kCountKPT) {
-                key = sk[r * kCountThreads];
-                ++r;
+            for (int r = 0; r < kCountKPT; r++) wq[r * 32 + lane] = nk[r];
+            __syncwarp();
+            qpos = 0;
+            c += W;
+            more = c * kCountChunk < total;
+            if (more) load_chunk(c);
+        }
+        const u32 need = __ballot_sync(0xFFFFFFFFu, key == 0);
+        if (key == 0) {
+            const u32 idx = qpos + __popc(need & lt_mask);
+            if (idx < (u32)kCountChunk) {
+                key = wq[idx];
                 off = (u32)(key >> off_shift) & rmask;
                 left = R;
             }
-            if (!__any_sync(0xFFFFFFFFu, key != 0 || r < (u32)kCountKPT)) break;
-            if (key != 0) {
-                u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
-                if (cur == 0) {
-                    cur = atomicCAS(ks + off, 0ull, key);
-                    if (cur == 0) { ++my_new; cur = key; }
-                }
-                if (cur == key) {
-                    atomicAdd(ds + off, 1u);
-                    key = 0;
-                } else {
-                    off = (off + 1) & rmask;
-                    if (--left == 0) { ++overflow; key = 0; }          // the region is full
-                }
+        }
+        qpos += __popc(need);
+        if (!__any_sync(0xFFFFFFFFu, key != 0)) {
+            if (qpos >= (u32)kCountChunk && !more) break;
+            continue;                            // only padding was fetched, or a refill is due
+        }
+        if (key != 0) {
+            u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
+            if (cur == 0) {
+                cur = atomicCAS(ks + off, 0ull, key);
+                if (cur == 0) { ++my_new; cur = key; }
+            }
+            if (cur == key) {
+                atomicAdd(ds + off, 1u);
+                key = 0;
+            } else {
+                off = (off + 1) & rmask;
+                if (--left == 0) { ++overflow; key = 0; }          // the region is full
             }
         }
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < R; i += kCountThreads) {
+    for (u32 i = threadIdx.x; i < R; i += THREADS) {
         const u32 d = ds[i];
         if (d) {
             const ulonglong2 old = gslots[i];
@@ -633,6 +670,13 @@ static bool use_deferred(const ssq_counter *c, int64_t n) {
 
 int scatter_grid(ssq_ctx *ctx, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
 
+// development tunables (read once per process)
+static int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    int v = e ? atoi(e) : dflt;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 // Size the level-1 partition buffers for a pass of n keys scattered by `grid` persistent CTAs.
 static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     ssq_ctx *ctx = c->ctx;
@@ -661,6 +705,9 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     pv->seg_count = c->part_cursor;
     pv->seg_cap = (u32)per;
     pv->num_ctas = (u32)grid;
+    // a tile brings 512 keys = 2 per partition on average and a ring holds 32: flushing every 4th tile keeps ring
+    // overflow (handled, but slow) below one key in a thousand tiles
+    pv->flush_every = (u32)env_int("SSQ_FLUSH_EVERY", 4, 1, 8);
     return SSQ_OK;
 }
 
@@ -672,12 +719,7 @@ static bool regions_fit_smem(const ssq_counter *c) {
 
 static int region_slices() {
     static int v = 0;
-    if (v == 0) {
-        const char *e = getenv("SSQ_REGION_SLICES");
-        v = e ? atoi(e) : 6;
-        if (v < 1) v = 1;
-        if (v > kMaxStreamSegs) v = kMaxStreamSegs;
-    }
+    if (v == 0) v = env_int("SSQ_REGION_SLICES", 6, 1, 8);
     return v;
 }
 
@@ -742,10 +784,24 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     region_scatter_kernel<<<kParts * rp.slices, kThreads, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
     SSQ_LAUNCH_CHECK();
     if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
-    const size_t region_bytes = count_regions_smem(t.log2_region);
-    rc = set_max_smem((const void *)count_regions_kernel, region_bytes);
-    if (rc) return rc;
-    count_regions_kernel<<<1u << (t.log2_cap - t.log2_region), kCountThreads, region_bytes, ctx->stream>>>(t, rp);
+    const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
+    const int cthreads = env_int("SSQ_COUNT_THREADS", 384, 256, 512);
+    if (cthreads == 256) {
+        const size_t bytes = count_regions_smem<256>(t.log2_region);
+        rc = set_max_smem((const void *)count_regions_kernel<256>, bytes);
+        if (rc) return rc;
+        count_regions_kernel<256><<<nregions, 256, bytes, ctx->stream>>>(t, rp);
+    } else if (cthreads == 512) {
+        const size_t bytes = count_regions_smem<512>(t.log2_region);
+        rc = set_max_smem((const void *)count_regions_kernel<512>, bytes);
+        if (rc) return rc;
+        count_regions_kernel<512><<<nregions, 512, bytes, ctx->stream>>>(t, rp);
+    } else {
+        const size_t bytes = count_regions_smem<384>(t.log2_region);
+        rc = set_max_smem((const void *)count_regions_kernel<384>, bytes);
+        if (rc) return rc;
+        count_regions_kernel<384><<<nregions, 384, bytes, ctx->stream>>>(t, rp);
+    }
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -1017,7 +1073,12 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
     int log2_parts = 0;
     while ((1 << log2_parts) < n_parts) log2_parts++;
     u64 *cursors = nullptr;
-    SSQ_CUDA(cudaMallocAsync(&cursors, kMaxParts * sizeof(u64), st));
+    {
+        void *scratch = nullptr;
+        int rc0 = ctx_scratch(ctx, kMaxParts * sizeof(u64), &scratch);
+        if (rc0) return rc0;
+        cursors = (u64 *)scratch;
+    }
     SSQ_CUDA(cudaMemsetAsync(part_counts, 0, n_parts * sizeof(u64), st));
     TableView t = view_of(c);
     const int64_t cap = (int64_t)1 << c->log2_cap;
@@ -1036,7 +1097,6 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
     }
     count_launch(); count_launch(); count_launch();
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(cursors, st);
     if (e != cudaSuccess) return cuda_fail(e, "export kernels", __FILE__, __LINE__);
     return SSQ_OK;
 }

@@ -31,6 +31,20 @@ bool debug_sync() {
     return v == 1;
 }
 
+int ctx_scratch(ssq_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        SSQ_CUDA(cudaDeviceSynchronize());
+        if (ctx->scratch) SSQ_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes + bytes / 2;
+        SSQ_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return SSQ_OK;
+}
+
 __global__ void reset_report_kernel(DevReport *r) {
     r->first_bad_base = kNoIndex;
     r->first_bad_len = kNoIndex;
@@ -92,6 +106,12 @@ int ssq_ctx_destroy(ssq_ctx *ctx) {
     if (!ctx) return SSQ_OK;
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < 2; b++) {
+        ssq_host_staging &st = ctx->staging;
+        cudaFree(st.ascii[b]); cudaFree(st.offsets[b]); cudaFree(st.lens_in[b]); cudaFree(st.words[b]); cudaFree(st.lens[b]);
+        if (st.events) { cudaEventDestroy(st.ev_in[b]); cudaEventDestroy(st.ev_out[b]); }
+    }
+    cudaFree(ctx->scratch);
     cudaFree(ctx->d_report);
     cudaFreeHost(ctx->h_report);
     for (int i = 0; i < 2; i++) cudaStreamDestroy(ctx->copy_streams[i]);

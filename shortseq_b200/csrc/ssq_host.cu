@@ -13,21 +13,45 @@ using namespace ssq;
 
 namespace {
 
-struct Staging {
-    uint8_t *ascii[2] = {nullptr, nullptr};
-    int64_t *offsets[2] = {nullptr, nullptr};
-    uint8_t *lens_in[2] = {nullptr, nullptr};
-    u64 *words[2] = {nullptr, nullptr};
-    uint8_t *lens[2] = {nullptr, nullptr};
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    ~Staging() {
+// Make the context's staging buffers large enough for chunks of `reads` reads / `ascii_bytes` bytes / `words` words.
+int ensure_staging(ssq_ctx *ctx, size_t ascii_bytes, size_t reads, size_t word_entries, bool by_lens, int nbuf) {
+    ssq_host_staging &st = ctx->staging;
+    if (!st.events) {
         for (int b = 0; b < 2; b++) {
-            cudaFree(ascii[b]); cudaFree(offsets[b]); cudaFree(lens_in[b]); cudaFree(words[b]); cudaFree(lens[b]);
-            if (ev_in[b]) cudaEventDestroy(ev_in[b]);
-            if (ev_out[b]) cudaEventDestroy(ev_out[b]);
+            SSQ_CUDA(cudaEventCreateWithFlags(&st.ev_in[b], cudaEventDisableTiming));
+            SSQ_CUDA(cudaEventCreateWithFlags(&st.ev_out[b], cudaEventDisableTiming));
+        }
+        st.events = true;
+    }
+    const bool grow_ascii = ascii_bytes > st.ascii_bytes, grow_reads = reads > st.reads, grow_words = word_entries > st.word_entries;
+    if (grow_ascii || grow_reads || grow_words) SSQ_CUDA(cudaDeviceSynchronize());    // nothing may still be using the old buffers
+    for (int b = 0; b < 2; b++) {
+        if (grow_ascii) {
+            if (st.ascii[b]) SSQ_CUDA(cudaFree(st.ascii[b]));
+            st.ascii[b] = nullptr;
+            SSQ_CUDA(cudaMalloc(&st.ascii[b], ascii_bytes + 16));
+        }
+        if (grow_reads) {
+            if (st.offsets[b]) SSQ_CUDA(cudaFree(st.offsets[b]));
+            if (st.lens_in[b]) SSQ_CUDA(cudaFree(st.lens_in[b]));
+            if (st.lens[b]) SSQ_CUDA(cudaFree(st.lens[b]));
+            st.offsets[b] = nullptr; st.lens_in[b] = nullptr; st.lens[b] = nullptr;
+            SSQ_CUDA(cudaMalloc(&st.offsets[b], sizeof(int64_t) * (reads + 1)));
+            SSQ_CUDA(cudaMalloc(&st.lens_in[b], reads));
+            SSQ_CUDA(cudaMalloc(&st.lens[b], reads));
+        }
+        if (grow_words) {
+            if (st.words[b]) SSQ_CUDA(cudaFree(st.words[b]));
+            st.words[b] = nullptr;
+            SSQ_CUDA(cudaMalloc(&st.words[b], sizeof(u64) * word_entries));
         }
     }
-};
+    if (grow_ascii) st.ascii_bytes = ascii_bytes;
+    if (grow_reads) st.reads = reads;
+    if (grow_words) st.word_entries = word_entries;
+    (void)by_lens; (void)nbuf;
+    return SSQ_OK;
+}
 
 int64_t sum_u8(const uint8_t *p, int64_t n) {
     int64_t s = 0;
@@ -63,17 +87,12 @@ int host_pipeline(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii, const in
     }
     SSQ_ARG(max_bytes == 0 || h_ascii != nullptr, "h_ascii is NULL");
 
-    Staging st;
     const bool want_words = h_words != nullptr, want_lens = h_lens != nullptr;
-    for (int b = 0; b < (nchunks > 1 ? 2 : 1); b++) {
-        SSQ_CUDA(cudaMalloc(&st.ascii[b], (size_t)max_bytes + 16));
-        SSQ_CUDA(cudaMalloc(&st.offsets[b], sizeof(int64_t) * (size_t)(chunk_reads + 1)));
-        if (by_lens) SSQ_CUDA(cudaMalloc(&st.lens_in[b], (size_t)chunk_reads));
-        SSQ_CUDA(cudaMalloc(&st.words[b], sizeof(u64) * (size_t)chunk_reads * W));
-        SSQ_CUDA(cudaMalloc(&st.lens[b], (size_t)chunk_reads));
-        SSQ_CUDA(cudaEventCreateWithFlags(&st.ev_in[b], cudaEventDisableTiming));
-        SSQ_CUDA(cudaEventCreateWithFlags(&st.ev_out[b], cudaEventDisableTiming));
+    {
+        int rc0 = ensure_staging(ctx, (size_t)max_bytes, (size_t)chunk_reads, (size_t)chunk_reads * W, by_lens, nchunks > 1 ? 2 : 1);
+        if (rc0) return rc0;
     }
+    ssq_host_staging &st = ctx->staging;
     cudaStream_t s_in = ctx->copy_streams[0], s_out = ctx->copy_streams[1], s_run = ctx->stream;
 
     int64_t byte_pos = 0;          // by_lens: running byte position of the next chunk to copy in

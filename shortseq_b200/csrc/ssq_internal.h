@@ -6,6 +6,19 @@
 #include "../../include/shortseq_b200.h"
 #include "ssq_device.cuh"
 
+// Device staging buffers of the host-buffer pipeline (ssq_host.cu): allocated on first use, grown when a call
+// needs more, released with the context -- cudaMalloc/cudaFree per call cost more than the copies they stage.
+struct ssq_host_staging {
+    uint8_t *ascii[2];
+    int64_t *offsets[2];
+    uint8_t *lens_in[2];
+    ssq::u64 *words[2];
+    uint8_t *lens[2];
+    size_t ascii_bytes, reads, word_entries;   // current capacities (per buffer)
+    cudaEvent_t ev_in[2], ev_out[2];
+    bool events;
+};
+
 struct ssq_ctx {
     int device;
     int sm_count;
@@ -14,6 +27,9 @@ struct ssq_ctx {
     cudaStream_t copy_streams[2]; // host pipeline: H2D / D2H
     ssq::DevReport *d_report;     // device error record
     ssq::DevReport *h_report;     // pinned mirror
+    ssq_host_staging staging;     // zero-initialised
+    void *scratch;                // small device scratch (scan block totals, export cursors); grown on demand
+    size_t scratch_bytes;
 };
 
 struct ssq_counter {
@@ -80,6 +96,11 @@ inline int grid_for(const ssq_ctx *ctx, int64_t work_items, int ctas_per_sm) {
     if (g < 1) g = 1;
     return (int)g;
 }
+
+// Device scratch of at least `bytes` bytes, valid until the next call that asks for more (work using it must be
+// enqueued on ctx->stream).  Growing synchronises the device; cudaMallocAsync is avoided on purpose: its pool is
+// trimmed at every stream synchronisation, which made per-chunk allocations cost milliseconds.
+int ctx_scratch(ssq_ctx *ctx, size_t bytes, void **out);
 
 // fused pack+count over a (possibly staged) slice (ssq_counter.cu)
 int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets, int64_t n,

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
     }
 
     u32 my_new = 0;
+    u32 since_flush = 0;
     const int64_t ntiles = (a.n + kTileReads - 1) / kTileReads;
     const int64_t stride = gridDim.x;
     int64_t tile = blockIdx.x;
@@ -309,8 +310,12 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
                 }
             }
             if constexpr (MODE == kModeScatter) {
-                __syncthreads();
-                flush_lines<false>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                // every flush_every-th tile: move the complete 128-byte lines of the staging rings to global memory
+                if (++since_flush >= pv.flush_every) {
+                    since_flush = 0;
+                    __syncthreads();
+                    flush_lines<false>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                }
             }
         }
         __syncthreads();   // codes[] / srel[] are rewritten by the next tile

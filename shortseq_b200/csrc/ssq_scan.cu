@@ -92,32 +92,47 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(F f, int64_t n
     if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = run;
 }
 
-template <class F>
-static int scan_exclusive(ssq_ctx *ctx, F f, int64_t n, int64_t *out /*[n+1]*/) {
-    cudaStream_t st = ctx->stream;
-    if (n <= 0) {
-        SSQ_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), st));
-        return SSQ_OK;
+// scratch entries (int64) a scan of n elements needs for its block totals, all levels
+static int64_t scan_scratch_entries(int64_t n) {
+    int64_t total = 0;
+    while (n > kScanTile) {
+        const int64_t nblocks = (n + kScanTile - 1) / kScanTile;
+        total += 2 * nblocks + 2;
+        n = nblocks;
     }
+    return total;
+}
+
+template <class F>
+static int scan_level(ssq_ctx *ctx, F f, int64_t n, int64_t *out /*[n+1]*/, int64_t *scratch) {
+    cudaStream_t st = ctx->stream;
     int64_t nblocks = (n + kScanTile - 1) / kScanTile;
     if (nblocks == 1) {
         scan_apply_kernel<<<1, kScanThreads, 0, st>>>(f, n, (const int64_t *)nullptr, out, true);
         SSQ_LAUNCH_CHECK();
         return SSQ_OK;
     }
-    int64_t *totals = nullptr;   // [nblocks] totals, then [nblocks+1] scanned
-    SSQ_CUDA(cudaMallocAsync(&totals, sizeof(int64_t) * (2 * nblocks + 2), st));
+    int64_t *totals = scratch;            // [nblocks] totals, then [nblocks+1] scanned (+1 pad)
     int64_t *scanned = totals + nblocks;
     scan_totals_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>>(f, n, totals);
     SSQ_LAUNCH_CHECK();
-    int rc = scan_exclusive(ctx, I64{totals}, nblocks, scanned);
-    if (rc == SSQ_OK) {
-        scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>>(f, n, scanned, out, true);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "scan_apply_kernel", __FILE__, __LINE__);
+    int rc = scan_level(ctx, I64{totals}, nblocks, scanned, scratch + 2 * nblocks + 2);
+    if (rc) return rc;
+    scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>>(f, n, scanned, out, true);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+template <class F>
+static int scan_exclusive(ssq_ctx *ctx, F f, int64_t n, int64_t *out /*[n+1]*/) {
+    if (n <= 0) {
+        SSQ_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), ctx->stream));
+        return SSQ_OK;
     }
-    cudaFreeAsync(totals, st);
-    return rc;
+    void *scratch = nullptr;
+    int rc = ctx_scratch(ctx, sizeof(int64_t) * (size_t)(scan_scratch_entries(n) + 2), &scratch);
+    if (rc) return rc;
+    return scan_level(ctx, f, n, out, (int64_t *)scratch);
 }
 
 int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out) {

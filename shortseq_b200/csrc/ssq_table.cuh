@@ -44,6 +44,7 @@ struct PartView {
     u32 *seg_count;     // [num_ctas][kParts] entries per segment (written when the scatter CTA finishes)
     u32 seg_cap;        // entries per segment (multiple of kLineKeys); keys beyond it are inserted directly by the scatter pass
     u32 num_ctas;       // grid size of the scatter pass
+    u32 flush_every;    // fused pack+scatter: tiles between two flushes of the staging rings
 };
 // Level-2 buffers: CTA (p, s) of the second scatter -- slice s of level-1 partition p -- owns the segments
 // keys[((p * slices + s) * kParts + r) * seg_cap ...] of the level-2 partitions r (hash bits 55..48) of partition p.
