@@ -15,8 +15,10 @@ of the number of distinct keys.
   e2e       same metric through the host-buffer C-ABI call ssq_host_pack_count_lens: pinned host ASCII + one
             uint8 length per read in, packed words out, host<->device copies inside the timed region (a
             bounded slice of the workload, size in e2e.reads_per_step)
-  roofline  fused pack+count kernel: algorithmic bytes (L+8+8W+1 per read + 8W+9 per unique)
-            / CUDA-event time of its launches, against MEASURED_PEAKS.json hbm_gbs
+  roofline  dominant kernel of the pass (most device time): algorithmic bytes per launch / its
+            CUDA-event time (events recorded inside the library on the launching stream), against
+            MEASURED_PEAKS.json hbm_gbs; "pass" = the whole fused pass (L+8+8W+1 per read + 8W+9 per unique),
+            "kernels" = every kernel of the pass; traffic = DRAM bytes per launch from the committed ncu capture
   cpu_baseline / --impl reference: the unmodified reference (oracle/_ref, Cython) on the host cores
 
 Only this file's cpu_baseline / --impl reference legs touch oracle/; the measured path never does.
@@ -235,7 +237,8 @@ def hbm_peak():
 
 
 def ncu_traffic():
-    """Per-launch DRAM traffic of the fused kernel from the committed ncu capture, if any."""
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full at the bench's full size)
+    of each kernel of the pass from the committed capture, if any: {kernel name: bytes, "pass": bytes}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -290,9 +293,9 @@ def run_ours(args):
         e0.record()
         _lib.check(lib.ssq_counter_pack_count(local.handle, ptr(batch.ascii), nbytes, ptr(batch.offsets), n, ptr(words), ptr(lens)))
         e1.record()
-        p1, p2 = C.c_float(), C.c_float()
-        _lib.check(lib.ssq_counter_last_pass_ms(local.handle, C.byref(p1), C.byref(p2)))   # CUDA events inside the library
-        phase_ms.append((p1.value, p2.value))
+        d = [C.c_float(), C.c_float(), C.c_float()]
+        _lib.check(lib.ssq_counter_last_pass_detail(local.handle, C.byref(d[0]), C.byref(d[1]), C.byref(d[2])))   # CUDA events inside the library
+        phase_ms.append(tuple(x.value for x in d))
         if world > 1:
             _lib.check(lib.ssq_counter_clear(owner.handle))
             merge_alltoall(local, owner=owner)
@@ -335,32 +338,47 @@ def run_ours(args):
     ms_per_step = total_ms / K
     value = world * n * L / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant kernel (fused pack+count), this rank
+    # roofline (this rank).  Algorithmic bytes are SURVEY 8d's: pack = ASCII + offset in, words + len out;
+    # count = the packed keys in, one (key, len, count) tuple per distinct key out.
     peak, peak_src = hbm_peak()
-    alg_bytes = n * (L + 8 + 8 * W + 1) + local_unique * (8 * W + 9)
+    pack_bytes = n * (L + 8 + 8 * W + 1)
+    count_bytes = n * (8 * W + 1) + local_unique * (8 * W + 9)
+    alg_bytes = n * (L + 8 + 8 * W + 1) + local_unique * (8 * W + 9)       # the fused pass: packed keys never re-read algorithmically
     k_ms = statistics.mean(kernel_ms)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    p1_ms = statistics.mean(p[0] for p in phase_ms)
-    p2_ms = statistics.mean(p[1] for p in phase_ms)
-    pack_bytes = n * (L + 8 + 8 * W + 1)                      # SURVEY 8d "pack": ASCII + offset in, words + len out
-    count_bytes = n * (8 * W + 1) + local_unique * (8 * W + 9)  # SURVEY 8d "count" on packed input
-    traffic = ncu_traffic()
-    deferred = p2_ms > 0
-    kernels = [{"kernel": f"ssq::pack_fixed_kernel<{W // 3},{2 if deferred else 1}> (pack + validate + "
-                          f"{'scatter keys to 256 hash partitions' if deferred else 'insert'})",
-                "ms_per_launch": round(p1_ms, 3), "launches_per_step": 1, "algorithmic_bytes_per_launch": pack_bytes if deferred else alg_bytes,
-                "achieved_gbs": round((pack_bytes if deferred else alg_bytes) / (p1_ms * 1e-3) / 1e9, 1)}]
+    p_ms = [statistics.mean(p[i] for p in phase_ms) for i in range(3)]
+    traffic = ncu_traffic() or {}
+    deferred = p_ms[1] + p_ms[2] > 0
+    regions = p_ms[1] > 0
+
+    def kern(name, what, ms, bytes_):
+        d = {"kernel": name, "what": what, "ms_per_launch": round(ms, 3), "launches_per_step": 1,
+             "algorithmic_bytes_per_launch": bytes_, "achieved_gbs": round(bytes_ / (ms * 1e-3) / 1e9, 1) if bytes_ else None,
+             "traffic": traffic.get(name.split("<")[0])}
+        d["frac"] = round(d["achieved_gbs"] / peak, 4) if bytes_ else None
+        return d
+
     if deferred:
-        kernels.append({"kernel": "ssq::count_parts_kernel (partition-ordered table insertion)", "ms_per_launch": round(p2_ms, 3),
-                        "launches_per_step": 1, "algorithmic_bytes_per_launch": count_bytes,
-                        "achieved_gbs": round(count_bytes / (p2_ms * 1e-3) / 1e9, 1)})
-    for kk in kernels:
-        kk["frac"] = round(kk["achieved_gbs"] / peak, 4)
-    # headline: the whole fused pass (its kernels back to back), algorithmic bytes of pack+count
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic.get("dram_bytes_per_step") if traffic else None,
-                "kernel": " + ".join(k["kernel"].split(" ")[0] for k in kernels) + " (one ssq_counter_pack_count pass)",
-                "peak_source": peak_src, "pass_ms": round(k_ms, 3), "algorithmic_bytes_per_pass": alg_bytes, "kernels": kernels}
+        kernels = [kern(f"ssq::pack_fixed_kernel<{W // 3},2>", "pack + validate + scatter keys to 256 hash partitions", p_ms[0], pack_bytes)]
+        if regions:
+            kernels.append(kern("ssq::region_scatter_kernel", "route keys to their 4096-slot table region (second 256-way scatter); "
+                                "shares the count phase's algorithmic bytes with count_regions_kernel", p_ms[1], 0))
+            kernels.append(kern("ssq::count_regions_kernel<384>", "count each region's keys in shared memory, write the table back",
+                                p_ms[2], count_bytes))
+            kernels[-1]["achieved_gbs"] = round(count_bytes / ((p_ms[1] + p_ms[2]) * 1e-3) / 1e9, 1)   # over both count-phase kernels
+            kernels[-1]["frac"] = round(kernels[-1]["achieved_gbs"] / peak, 4)
+        else:
+            kernels.append(kern("ssq::count_parts_kernel", "partition-ordered table insertion (L2-resident table ranges)", p_ms[2], count_bytes))
+    else:
+        kernels = [kern(f"ssq::pack_fixed_kernel<{W // 3},1>", "pack + validate + insert", p_ms[0], alg_bytes)]
+    dom = max(kernels, key=lambda kk: kk["ms_per_launch"])
+    # top level = the dominant kernel (most device time per step); "pass" = all kernels of one ssq_counter_pack_count
+    roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "kernel": dom["kernel"], "kernel_ms_per_launch": dom["ms_per_launch"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "peak_source": peak_src,
+                "pass": {"kernels": " + ".join(kk["kernel"] for kk in kernels), "ms": round(k_ms, 3), "algorithmic_bytes": alg_bytes,
+                         "achieved": round(alg_bytes / (k_ms * 1e-3) / 1e9, 1), "frac": round(alg_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
+                         "traffic": traffic.get("pass")},
+                "kernels": kernels}
 
     # e2e: host buffers through the C ABI
     e2e = None

@@ -29,15 +29,20 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: development variants (e.g. -DSSQ_LINE_KEYS=8 into variants/libssq_line8.so, loaded with
+    SSQ_LIB=...); the product library is always built without defines."""
+    lib = LIB if out is None else os.path.join(HERE, "variants", out)
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs, procs = [], []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if out is None else os.path.join("build", out))
+    os.makedirs(bdir, exist_ok=True)
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd)))
@@ -45,9 +50,11 @@ def build(force=False, verbose=False):
     for src, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed for {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

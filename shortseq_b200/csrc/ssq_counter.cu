@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) rehash_kernel(TableView src, TableVi
 // Tables whose regions do not fit in shared memory (>= 2^30 slots) fall back to count_parts_kernel, which inserts
 // level-1 partitions in order so that the table range being hit (cap/256 slots) stays resident in L2.
 constexpr int kCountKeysPerThread = 8;
-constexpr int kScatterRounds = 4;    // keys per thread between flushes
+constexpr int kScatterRounds = kLineKeys / 4;    // keys per thread between flushes (mean 4 per 32-key ring)
 
 // Level 1 for already packed input.
 __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t, PartView pv, const u64 *words,
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[kParts], s_tail[kParts];
     __shared__ u32 s_new[kThreads / 32];
+    __shared__ u32 s_list[(kThreads / 32) * 64];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail};
+    const Stager stg{dyn_ring, s_head, s_tail, s_list};
     u64 *const seg0 = pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap;
     stager_init(stg);
     if (threadIdx.x == 0) s_unstaged_new = 0;
@@ -208,8 +209,9 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[kParts], s_tail[kParts];
     __shared__ u32 pre[kMaxStreamSegs + 1];
+    __shared__ u32 s_list[(kThreads / 32) * 64];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail};
+    const Stager stg{dyn_ring, s_head, s_tail, s_list};
     const u32 p = blockIdx.x / rp.slices, s = blockIdx.x - p * rp.slices;
     const u32 c0 = (u32)((u64)pv.num_ctas * s / rp.slices), c1 = (u32)((u64)pv.num_ctas * (s + 1) / rp.slices);
     const u32 nseg = c1 - c0;
@@ -231,37 +233,42 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
         if (lane == 0) pre[0] = 0;
     }
     __syncthreads();
-    const u32 total = pre[nseg];
     const u64 drop = l2_policy_evict_first();
     const u64 *const part0 = pv.keys + ((size_t)c0 * kParts + p) * pv.seg_cap;     // segment k starts at part0 + k * seg_stride
     const size_t seg_stride = (size_t)kParts * pv.seg_cap;
-    u32 seg = 0;
+    constexpr u32 kTile = kThreads * kScatterRounds;
+    // Tiles never straddle segments, so a tile's keys sit at consecutive addresses.  (seg, pos) = where the next tile
+    // to LOAD starts; both are CTA-uniform.
+    u32 seg = 0, pos = 0;
     u64 nk[kScatterRounds];
-    auto load_tile = [&](u32 i0) {
+    auto load_tile = [&]() -> u32 {             // returns the number of keys of the tile (0 = stream exhausted)
+        while (seg < nseg && pos >= pre[seg + 1] - pre[seg]) { ++seg; pos = 0; }
+        if (seg >= nseg) return 0u;
+        const u32 here = min(pre[seg + 1] - pre[seg] - pos, kTile);
+        const u64 *src = part0 + seg * seg_stride + pos + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < kScatterRounds; j++) {
-            const u32 i = i0 + j * kThreads + threadIdx.x;
-            nk[j] = 0;
-            if (i < total) {
-                while (i >= pre[seg + 1]) ++seg;
-                nk[j] = ld_stream_u64(part0 + seg * seg_stride + (i - pre[seg]), drop);
-            }
-        }
+        for (int j = 0; j < kScatterRounds; j++) nk[j] = (u32)(j * kThreads) + threadIdx.x < here ? ld_stream_u64(src + j * kThreads, drop) : 0ull;
+        pos += here;
+        return here;
     };
-    if (total) load_tile(0);
-    for (u32 i0 = 0; i0 < total; i0 += kThreads * kScatterRounds) {
+    u32 have = load_tile(), unflushed = 0;
+    while (have) {
         u64 k[kScatterRounds];
 #pragma unroll
         for (int j = 0; j < kScatterRounds; j++) k[j] = nk[j];
-        if (i0 + kThreads * kScatterRounds < total) load_tile(i0 + kThreads * kScatterRounds);
+        unflushed += have;
+        have = load_tile();                      // in flight while this tile is staged and flushed
 #pragma unroll
         for (int j = 0; j < kScatterRounds; j++) {
             if (k[j] == 0) continue;
             if (!stage_key(stg, (u32)(k[j] >> 48) & 0xFFu, k[j])) insert_unstaged(t, k[j], p, &s_unstaged_new);
         }
-        __syncthreads();
-        flush_lines<false>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
-        __syncthreads();
+        if (unflushed >= kTile / 2 || !have) {   // a short tail tile waits for the next one
+            unflushed = 0;
+            __syncthreads();
+            flush_lines<false>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
+            __syncthreads();
+        }
     }
     flush_lines<true>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
     __syncthreads();
@@ -279,17 +286,17 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
 // L2, where the region load asked it to stay).
 constexpr int kCountKPT = 8;
 constexpr int kCountChunk = 32 * kCountKPT;
+constexpr int kMaxRegionSegs = 384;      // slices (<= 6 counted here; more only with 1:1 regions) x level-2 partitions per region (<= 64)
 
 template <int THREADS>
-static size_t count_regions_smem(int log2_region) {
-    return ((size_t)12 << log2_region) + sizeof(u64) * kCountKPT * THREADS;
+static size_t count_regions_smem(int log2_region, unsigned nseg) {
+    return ((size_t)12 << log2_region) + sizeof(u64) * kCountKPT * THREADS + sizeof(u32) * (2 * nseg + 2);
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3)
 count_regions_kernel(TableView t, RegionParts rp) {
     extern __shared__ __align__(16) u64 dyn_region[];
-    __shared__ u32 pre[kMaxStreamSegs + 1];
     __shared__ u32 s_new[THREADS / 32];
     constexpr u32 W = THREADS / 32;
     const u32 R = 1u << t.log2_region, rmask = R - 1;
@@ -297,6 +304,8 @@ count_regions_kernel(TableView t, RegionParts rp) {
     u32 *ds = reinterpret_cast<u32 *>(dyn_region + R);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *wq = dyn_region + R + R / 2 + warp * kCountChunk;     // this warp's key queue
+    u32 *pre = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + W * kCountChunk);   // [nseg + 1] exclusive scan of the segment sizes
+    u32 *segoff = pre + (rp.slices << (8 - rp.qbits)) + 1;                          // [nseg] first entry of stream segment k in rp.keys
     const u32 region = blockIdx.x;
     const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
     const u32 p = region >> rp.qbits, q = region & ((1u << rp.qbits) - 1);
@@ -310,7 +319,10 @@ count_regions_kernel(TableView t, RegionParts rp) {
             u32 incl = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
-            if (k < nseg) pre[k + 1] = carry + incl;
+            if (k < nseg) {
+                pre[k + 1] = carry + incl;
+                segoff[k] = (u32)(seg_index(k) * rp.seg_cap);      // the host checked that the buffer has < 2^32 entries
+            }
             carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
         if (lane == 0) pre[0] = 0;
@@ -334,7 +346,7 @@ count_regions_kernel(TableView t, RegionParts rp) {
             nk[r] = 0;
             if (i < total) {
                 while (i >= pre[seg + 1]) ++seg;
-                nk[r] = ld_stream_u64(rp.keys + seg_index(seg) * rp.seg_cap + (i - pre[seg]), drop);
+                nk[r] = ld_stream_u64(rp.keys + (segoff[seg] + (i - pre[seg])), drop);
             }
         }
     };
@@ -719,7 +731,7 @@ static bool regions_fit_smem(const ssq_counter *c) {
 
 static int region_slices() {
     static int v = 0;
-    if (v == 0) v = env_int("SSQ_REGION_SLICES", 6, 1, 8);
+    if (v == 0) v = env_int("SSQ_REGION_SLICES", 6, 1, 6);
     return v;
 }
 
@@ -729,7 +741,7 @@ static int prepare_regions(ssq_counter *c, int64_t n, RegionParts *rp) {
     const int lr = region_bits_for(c->log2_cap);
     const int qbits = c->log2_cap - 8 - lr;
     const int slices = region_slices();
-    if ((slices << (8 - qbits)) > kMaxStreamSegs) { set_error("too many level-2 segments per region"); return SSQ_ERR_ARG; }
+    if ((slices << (8 - qbits)) > kMaxRegionSegs) { set_error("too many level-2 segments per region"); return SSQ_ERR_ARG; }
     int64_t per = n / ((int64_t)kParts * slices * kParts);
     per = per + per / 16 + 64;
     per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
@@ -770,7 +782,9 @@ static int set_max_smem(const void *kernel, size_t bytes) {
 static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cudaEvent_t ev_mid) {
     ssq_ctx *ctx = c->ctx;
     const TableView t = view_of(c);
-    if (!regions_fit_smem(c) || pv.num_ctas > (u32)kMaxStreamSegs) {
+    // the count kernel addresses the level-2 buffer with 32-bit entry offsets
+    const bool small_enough = (double)n * 1.07 + 64.0 * kParts * kParts * region_slices() < 4.0e9;
+    if (!regions_fit_smem(c) || pv.num_ctas > (u32)kMaxStreamSegs || !small_enough || env_int("SSQ_FORCE_L2_COUNT", 0, 0, 1)) {
         if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
         count_parts_kernel<<<kParts * pv.num_ctas, kThreads, 0, ctx->stream>>>(t, pv);
         SSQ_LAUNCH_CHECK();
@@ -785,19 +799,20 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     SSQ_LAUNCH_CHECK();
     if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
     const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
+    const unsigned nseg = rp.slices << (8 - rp.qbits);
     const int cthreads = env_int("SSQ_COUNT_THREADS", 384, 256, 512);
     if (cthreads == 256) {
-        const size_t bytes = count_regions_smem<256>(t.log2_region);
+        const size_t bytes = count_regions_smem<256>(t.log2_region, nseg);
         rc = set_max_smem((const void *)count_regions_kernel<256>, bytes);
         if (rc) return rc;
         count_regions_kernel<256><<<nregions, 256, bytes, ctx->stream>>>(t, rp);
     } else if (cthreads == 512) {
-        const size_t bytes = count_regions_smem<512>(t.log2_region);
+        const size_t bytes = count_regions_smem<512>(t.log2_region, nseg);
         rc = set_max_smem((const void *)count_regions_kernel<512>, bytes);
         if (rc) return rc;
         count_regions_kernel<512><<<nregions, 512, bytes, ctx->stream>>>(t, rp);
     } else {
-        const size_t bytes = count_regions_smem<384>(t.log2_region);
+        const size_t bytes = count_regions_smem<384>(t.log2_region, nseg);
         rc = set_max_smem((const void *)count_regions_kernel<384>, bytes);
         if (rc) return rc;
         count_regions_kernel<384><<<nregions, 384, bytes, ctx->stream>>>(t, rp);

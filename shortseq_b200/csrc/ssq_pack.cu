@@ -181,8 +181,11 @@ __device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets,
 // extracted, the 16-byte loads of the CTA's next tile and the offsets of the one after are already in flight.
 // Three resident CTAs per SM (<= 85 registers) measured best on B200: two lose latency hiding, four (<= 64
 // registers) spill the prefetch state.
+#ifndef SSQ_PACK_MIN_BLOCKS
+#define SSQ_PACK_MIN_BLOCKS 3
+#endif
 template <int KLASS, int MODE>
-__global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+__global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     constexpr int MAXLEN = KLASS == SSQ_CLASS_64 ? 32 : 96;
     constexpr int MINLEN = KLASS == SSQ_CLASS_64 ? 0 : 33;
     constexpr int W = KLASS == SSQ_CLASS_64 ? 1 : 3;
@@ -196,8 +199,9 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_fixed_kernel(PackArgs a,
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail};
+    const Stager stg{dyn_ring, s_head, s_tail, s_list};
     u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;

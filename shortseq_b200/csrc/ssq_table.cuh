@@ -36,7 +36,10 @@ constexpr int kMinLog2Cap = 16;
 // Isolated 8-byte stores to 256 different places cost one memory transaction each (scripts/bench_scatter.cu);
 // keys are therefore staged per partition in shared memory and written as whole 128-byte lines (see Stager).
 constexpr int kParts = 256;
-constexpr int kLineKeys = 16;        // keys per flushed line (128 bytes)
+#ifndef SSQ_LINE_KEYS
+#define SSQ_LINE_KEYS 16
+#endif
+constexpr int kLineKeys = SSQ_LINE_KEYS;   // keys per flushed line (16 keys = 128 bytes)
 constexpr int kRingKeys = 2 * kLineKeys;   // staging ring per partition per CTA
 constexpr size_t kStagerRingBytes = (size_t)kParts * kRingKeys * sizeof(u64);   // 64 KB of dynamic shared memory
 struct PartView {
@@ -195,6 +198,7 @@ struct Stager {
     u64 *ring;     // [kParts][kRingKeys]
     u32 *head;     // [kParts]
     u32 *tail;     // [kParts]
+    u32 *list;     // [warps][64] scratch of flush_lines
 };
 
 __device__ __forceinline__ void stager_init(const Stager &s) {
@@ -228,35 +232,30 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
     constexpr u32 kGroups = 32 / kLaneGroup;            // lines per warp-wide store
     const u32 lane = threadIdx.x & 31;
     const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
+    const u32 lt_mask = (1u << lane) - 1;
+    u32 *const list = s.list + (threadIdx.x >> 5) * 64;   // this warp's work list: ready lines as (pass << 5 | lane)
     for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)kParts; pbase += blockDim.x) {
         const u32 p = pbase + lane;
         const u32 tl = s.tail[p];
         const u32 hd = min(s.head[p], tl + (u32)kRingKeys);
         const u32 avail = hd - tl;
         const u32 nl = avail / kLineKeys;               // 0, 1 or 2 complete lines
-#pragma unroll
-        for (u32 pass = 0; pass < 2; pass++) {
-            u32 m = __ballot_sync(0xFFFFFFFFu, nl > pass);
-            while (m) {
-                int bit = -1;
-#pragma unroll
-                for (u32 k = 0; k < kGroups; k++) {      // group k takes the k-th lowest ready partition
-                    const int b = __ffs(m) - 1;
-                    if (k == g) bit = b;
-                    m &= m - 1;
-                }
-                if (bit >= 0) {
-                    const u32 q = pbase + (u32)bit;
-                    const u32 tq = s.tail[q] + pass * kLineKeys;
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s.ring + q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub);
-                    if (tq + kLineKeys <= seg_cap) {
-                        *reinterpret_cast<ulonglong2 *>(seg0 + (size_t)q * seg_cap + tq + 2 * sub) = v;
-                    } else {                              // segment full
-                        const u32 top = fixed_top >= 0 ? (u32)fixed_top : q;
-                        insert_unstaged(t, v.x, top, s_new);
-                        insert_unstaged(t, v.y, top, s_new);
-                    }
-                }
+        const u32 m1 = __ballot_sync(0xFFFFFFFFu, nl > 0), m2 = __ballot_sync(0xFFFFFFFFu, nl > 1);
+        const u32 n1 = __popc(m1), nready = n1 + __popc(m2);
+        if (nl > 0) list[__popc(m1 & lt_mask)] = lane;
+        if (nl > 1) list[n1 + __popc(m2 & lt_mask)] = 32u | lane;
+        __syncwarp();
+        for (u32 it = g; it < nready; it += kGroups) {   // group g copies the lines it, it + kGroups, ...
+            const u32 e = list[it];
+            const u32 q = pbase + (e & 31u);
+            const u32 tq = s.tail[q] + (e >> 5) * kLineKeys;
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s.ring + q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub);
+            if (tq + kLineKeys <= seg_cap) {
+                *reinterpret_cast<ulonglong2 *>(seg0 + (size_t)q * seg_cap + tq + 2 * sub) = v;
+            } else {                                      // segment full
+                const u32 top = fixed_top >= 0 ? (u32)fixed_top : q;
+                insert_unstaged(t, v.x, top, s_new);
+                insert_unstaged(t, v.y, top, s_new);
             }
         }
         __syncwarp();

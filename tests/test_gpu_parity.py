@@ -360,6 +360,38 @@ def test_counter_deferred_partition_path(sq, oracle, fused):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
 
 
+def test_counter_deferred_l2_fallback(sq, oracle, monkeypatch):
+    """Tables whose regions do not fit in shared memory (>= 2^30 slots) count the level-1 partitions in order with
+    global atomics; SSQ_FORCE_L2_COUNT=1 takes that path on a small table."""
+    monkeypatch.setenv("SSQ_FORCE_L2_COUNT", "1")
+    n, u = 2_500_000, 1_200_000
+    b = sq.synth_reads(n, u, 20, 32, seed=0x5EED0011)
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, 0)
+    ctr = sq.DeviceCounter(0, expected_unique=2_000_000)
+    ctr.pack_count(b)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+
+
+@pytest.mark.parametrize("log2_slots", [23, 25])
+def test_counter_region_path_table_sizes(sq, oracle, log2_slots):
+    """The shared-memory region path with fewer than 256 regions per level-1 partition (tables below 2^28 slots):
+    a region then gathers several level-2 partitions."""
+    u = (1 << log2_slots) // 2 - 1000
+    n = max(3_000_000, (1 << log2_slots) // 3)
+    b = sq.synth_reads(n, n // 3, 25, 32, seed=0x5EED0021)
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, 0)
+    ctr = sq.DeviceCounter(0, expected_unique=u)
+    assert ctr.capacity() == 1 << log2_slots
+    ctr.pack_count(b)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+
+
 def test_counter_deferred_partition_overflow_and_growth(sq, oracle):
     """Half of the reads are one sequence: its hash partition overflows its buffer and the excess is inserted
     directly; the distinct keys exceed 60 % of the table, so it grows after the pass."""
