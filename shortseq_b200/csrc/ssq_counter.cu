@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t
     __shared__ u32 s_new[kThreads / 32];
     __shared__ u32 s_list[(kThreads / 32) * 64];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail, s_list};
+    const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     u64 *const seg0 = pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap;
     stager_init(stg);
     if (threadIdx.x == 0) s_unstaged_new = 0;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     __shared__ u32 pre[kMaxStreamSegs + 1];
     __shared__ u32 s_list[(kThreads / 32) * 64];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail, s_list};
+    const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     const u32 p = blockIdx.x / rp.slices, s = blockIdx.x - p * rp.slices;
     const u32 c0 = (u32)((u64)pv.num_ctas * s / rp.slices), c1 = (u32)((u64)pv.num_ctas * (s + 1) / rp.slices);
     const u32 nseg = c1 - c0;
@@ -354,44 +354,50 @@ count_regions_kernel(TableView t, RegionParts rp) {
     bool more = c * kCountChunk < total;         // warp-uniform: nk[] holds a chunk that is not yet in the queue
     if (more) load_chunk(c);
     u32 qpos = kCountChunk;                      // warp-uniform: next unread queue entry (>= kCountChunk: queue empty)
-    u32 off = 0, left = 0;
-    u64 key = 0;                                 // 0 = this lane is between keys
+    // The loop works on 32-bit shared-space addresses and on key halves.  A key's high word is never 0 (it holds
+    // len + 1 in bits 58..63), so `khi == 0` means "this lane is between keys" / "empty slot".  The home slot's
+    // region offset lies in the high word too: off_shift >= 32 for every table this kernel is launched on.
+    const u32 ks_a = smem_addr(ks), ds_a = smem_addr(ds), wq_a = smem_addr(wq);
+    const u32 hi_shift = (u32)off_shift - 32;
+    u32 klo = 0, khi = 0, off = 0, home = 0;
     for (;;) {
         if (qpos >= (u32)kCountChunk && more) {  // refill the queue, start the loads of the chunk after it
 #pragma unroll
-            for (int r = 0; r < kCountKPT; r++) wq[r * 32 + lane] = nk[r];
+            for (int r = 0; r < kCountKPT; r++) sts_u64(wq_a + (r * 32 + lane) * 8, nk[r]);
             __syncwarp();
             qpos = 0;
             c += W;
             more = c * kCountChunk < total;
             if (more) load_chunk(c);
         }
-        const u32 need = __ballot_sync(0xFFFFFFFFu, key == 0);
-        if (key == 0) {
+        const u32 need = __ballot_sync(0xFFFFFFFFu, khi == 0);
+        if (khi == 0) {
             const u32 idx = qpos + __popc(need & lt_mask);
             if (idx < (u32)kCountChunk) {
-                key = wq[idx];
-                off = (u32)(key >> off_shift) & rmask;
-                left = R;
+                lds_v2(wq_a + idx * 8, klo, khi);
+                home = off = (khi >> hi_shift) & rmask;
             }
         }
         qpos += __popc(need);
-        if (!__any_sync(0xFFFFFFFFu, key != 0)) {
+        if (!__any_sync(0xFFFFFFFFu, khi != 0)) {
             if (qpos >= (u32)kCountChunk && !more) break;
             continue;                            // only padding was fetched, or a refill is due
         }
-        if (key != 0) {
-            u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
-            if (cur == 0) {
-                cur = atomicCAS(ks + off, 0ull, key);
-                if (cur == 0) { ++my_new; cur = key; }
+        if (khi != 0) {
+            u32 clo, chi;
+            lds_v2(ks_a + off * 8, clo, chi);
+            if (chi == 0) {                      // empty slot: claim it
+                const u64 old = atoms_cas_u64(ks_a + off * 8, 0ull, ((u64)khi << 32) | klo);
+                clo = (u32)old;
+                chi = (u32)(old >> 32);
+                if (chi == 0) { ++my_new; clo = klo; chi = khi; }
             }
-            if (cur == key) {
-                atomicAdd(ds + off, 1u);
-                key = 0;
+            if (clo == klo && chi == khi) {
+                reds_add_u32(ds_a + off * 4, 1u);
+                khi = 0;
             } else {
                 off = (off + 1) & rmask;
-                if (--left == 0) { ++overflow; key = 0; }          // the region is full
+                if (off == home) { ++overflow; khi = 0; }          // went around: the region is full
             }
         }
     }

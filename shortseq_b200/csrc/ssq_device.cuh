@@ -100,6 +100,47 @@ __device__ __forceinline__ void red_min_u64(u64 *p, u64 v) {
     asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// ---- shared memory by 32-bit shared-space address ---------------------------------------------
+// Hot loops address shared memory through a 32-bit shared-space address computed once: with generic pointers the
+// compiler re-derives the shared window base (S2UR SR_CgaCtaId + ULEA ...) at every use inside the loop.
+// The address passes through an opaque asm so that it lives in a register instead of being rematerialised.
+__device__ __forceinline__ u32 smem_addr(const void *p) {
+    u32 a = (u32)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void lds_v2(u32 addr, u32 &lo, u32 &hi) {          // volatile: re-read every time
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ u32 lds_u32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(u32 addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 lds_u64(u32 addr) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ ulonglong2 lds_v2u64(u32 addr) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 atoms_cas_u64(u32 addr, u64 cmp, u64 val) {
+    u64 old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ u32 atoms_add_u32(u32 addr, u32 v) {
+    u32 old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add_u32(u32 addr, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
 // ---- 2-bit encoding -------------------------------------------------------------
 // Four ASCII bases in one 32-bit word -> 8 bits of 2-bit codes in the TOP byte
 // (code = (c>>1)&3: A0 C1 T2 G3, README.md:105-110 / util.pyx:39 of the reference).

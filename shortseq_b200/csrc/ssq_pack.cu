@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
     __shared__ u32 s_unstaged_new;
-    const Stager stg{dyn_ring, s_head, s_tail, s_list};
+    const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;

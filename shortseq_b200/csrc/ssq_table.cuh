@@ -194,23 +194,27 @@ __device__ __forceinline__ u64 find192(const TableView &t, u64 w0, u64 w1, u64 w
 // cursors (head = keys staged so far, tail = keys already flushed).  Keys leave the SM only as whole,
 // aligned LINES of kLineKeys keys (128 bytes), copied by kLineKeys/2 neighbouring lanes with one 16-byte
 // store each -- one full-line memory transaction per 16 keys instead of one per key.
-struct Stager {
-    u64 *ring;     // [kParts][kRingKeys]
-    u32 *head;     // [kParts]
-    u32 *tail;     // [kParts]
-    u32 *list;     // [warps][64] scratch of flush_lines
+struct Stager {      // 32-bit shared-space addresses (see smem_addr)
+    u32 ring;      // u64 [kParts][kRingKeys]
+    u32 head;      // u32 [kParts]
+    u32 tail;      // u32 [kParts]
+    u32 list;      // u32 [warps][64] scratch of flush_lines
 };
 
+__device__ __forceinline__ Stager make_stager(const u64 *ring, const u32 *head, const u32 *tail, const u32 *list) {
+    return Stager{smem_addr(ring), smem_addr(head), smem_addr(tail), smem_addr(list)};
+}
+
 __device__ __forceinline__ void stager_init(const Stager &s) {
-    for (u32 p = threadIdx.x; p < (u32)kParts; p += blockDim.x) { s.head[p] = 0; s.tail[p] = 0; }
+    for (u32 p = threadIdx.x; p < (u32)kParts; p += blockDim.x) { sts_u32(s.head + 4 * p, 0); sts_u32(s.tail + 4 * p, 0); }
 }
 
 // Append one key to partition `part`.  Returns false when the ring is full (more than kRingKeys keys of one
 // partition between two flushes: heavily skewed input); the caller then inserts the key directly.
 __device__ __forceinline__ bool stage_key(const Stager &s, u32 part, u64 key) {
-    const u32 pos = atomicAdd(&s.head[part], 1u);
-    if (pos - s.tail[part] >= (u32)kRingKeys) return false;     // flush_lines clamps head back
-    s.ring[part * kRingKeys + (pos & (kRingKeys - 1))] = key;
+    const u32 pos = atoms_add_u32(s.head + 4 * part, 1u);
+    if (pos - lds_u32(s.tail + 4 * part) >= (u32)kRingKeys) return false;     // flush_lines clamps head back
+    sts_u64(s.ring + 8 * (part * kRingKeys + (pos & (kRingKeys - 1))), key);
     return true;
 }
 
@@ -233,23 +237,23 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
     const u32 lane = threadIdx.x & 31;
     const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
     const u32 lt_mask = (1u << lane) - 1;
-    u32 *const list = s.list + (threadIdx.x >> 5) * 64;   // this warp's work list: ready lines as (pass << 5 | lane)
+    const u32 list = s.list + (threadIdx.x >> 5) * 256;  // this warp's work list: ready lines as (pass << 5 | lane)
     for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)kParts; pbase += blockDim.x) {
         const u32 p = pbase + lane;
-        const u32 tl = s.tail[p];
-        const u32 hd = min(s.head[p], tl + (u32)kRingKeys);
+        const u32 tl = lds_u32(s.tail + 4 * p);
+        const u32 hd = min(lds_u32(s.head + 4 * p), tl + (u32)kRingKeys);
         const u32 avail = hd - tl;
         const u32 nl = avail / kLineKeys;               // 0, 1 or 2 complete lines
         const u32 m1 = __ballot_sync(0xFFFFFFFFu, nl > 0), m2 = __ballot_sync(0xFFFFFFFFu, nl > 1);
         const u32 n1 = __popc(m1), nready = n1 + __popc(m2);
-        if (nl > 0) list[__popc(m1 & lt_mask)] = lane;
-        if (nl > 1) list[n1 + __popc(m2 & lt_mask)] = 32u | lane;
+        if (nl > 0) sts_u32(list + 4 * __popc(m1 & lt_mask), lane);
+        if (nl > 1) sts_u32(list + 4 * (n1 + __popc(m2 & lt_mask)), 32u | lane);
         __syncwarp();
         for (u32 it = g; it < nready; it += kGroups) {   // group g copies the lines it, it + kGroups, ...
-            const u32 e = list[it];
+            const u32 e = lds_u32(list + 4 * it);
             const u32 q = pbase + (e & 31u);
-            const u32 tq = s.tail[q] + (e >> 5) * kLineKeys;
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s.ring + q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub);
+            const u32 tq = lds_u32(s.tail + 4 * q) + (e >> 5) * kLineKeys;
+            const ulonglong2 v = lds_v2u64(s.ring + 8 * (q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub));
             if (tq + kLineKeys <= seg_cap) {
                 *reinterpret_cast<ulonglong2 *>(seg0 + (size_t)q * seg_cap + tq + 2 * sub) = v;
             } else {                                      // segment full
@@ -262,19 +266,19 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
         u32 flushed = nl * kLineKeys;
         if (FINAL) {                                      // the partial last line, key by key (once per CTA)
             for (u32 j = flushed; j < avail; j++) {
-                const u64 key = s.ring[p * kRingKeys + ((tl + j) & (kRingKeys - 1))];
+                const u64 key = lds_u64(s.ring + 8 * (p * kRingKeys + ((tl + j) & (kRingKeys - 1))));
                 if (tl + avail <= seg_cap) seg0[(size_t)p * seg_cap + tl + j] = key;
                 else insert_unstaged(t, key, fixed_top >= 0 ? (u32)fixed_top : p, s_new);
             }
             flushed = avail;
         }
-        s.tail[p] = tl + flushed;
-        s.head[p] = hd;
+        sts_u32(s.tail + 4 * p, tl + flushed);
+        sts_u32(s.head + 4 * p, hd);
     }
 }
 
 // entries of partition p's segment that were written to global memory (call after the FINAL flush + barrier)
-__device__ __forceinline__ u32 stager_seg_count(const Stager &s, u32 p, u32 seg_cap) { return min(s.tail[p], seg_cap); }
+__device__ __forceinline__ u32 stager_seg_count(const Stager &s, u32 p, u32 seg_cap) { return min(lds_u32(s.tail + 4 * p), seg_cap); }
 
 // Add the number of keys this warp created to the table's size counter with one atomic per warp.
 __device__ __forceinline__ void add_new_keys(const TableView &t, bool is_new) {
