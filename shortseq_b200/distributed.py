@@ -12,10 +12,25 @@ UNIQUES, not reads:
 The global counter is the disjoint union of the P owner tables.  The reference has no
 multi-process mode; this is new.
 """
+import os
+import time
+
 import torch
 import torch.distributed as dist
 
 from ._lib import CLASS_64
+
+_TIMING = os.environ.get("SSQ_MERGE_TIMING") == "1"      # development: print the wall time of each merge phase (adds syncs)
+
+
+def _tick(label, t0, ctx):
+    if not _TIMING:
+        return t0
+    torch.cuda.synchronize(ctx.device)
+    t1 = time.perf_counter()
+    if dist.get_rank() == 0:
+        print(f"  [merge] {label}: {(t1 - t0) * 1e3:.2f} ms", flush=True)
+    return t1
 
 
 def exchange_counts(send_counts, group=None):
@@ -51,15 +66,20 @@ def merge_alltoall(local, group=None, owner=None):
     if world & (world - 1):
         raise ValueError("merge_alltoall needs a power-of-two world size")
     rot = world.bit_length() - 1
+    t0 = _tick("start", time.perf_counter(), local.ctx) if _TIMING else 0.0
     keys, counts, _, parts = local.export(world)
+    t0 = _tick("export", t0, local.ctx)
     if world == 1:
         recv_w, recv_l, recv_c = keys.words, keys.lens, counts
     else:
         recv_counts = exchange_counts(parts, group)
+        t0 = _tick("exchange sizes", t0, local.ctx)
         recv_w, recv_l, recv_c = exchange_tuples(keys.words, keys.lens, counts, parts, recv_counts, group)
+        t0 = _tick("exchange tuples", t0, local.ctx)
     if owner is None:
         owner = DeviceCounter(local.klass, expected_unique=int(recv_l.numel()), hash_rot=rot, device=local.ctx.device)
     owner.merge(recv_w, recv_l, recv_c)
+    _tick("merge into owner table", t0, local.ctx)
     return owner
 
 
