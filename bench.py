@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-reads", type=float, default=2e6, help="reads per CPU-baseline step (per process)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange the uniques with NCCL all-to-all instead of peer stores")
     return ap.parse_args()
 
 
@@ -159,7 +160,9 @@ def config_of(args, world):
         "workload": f"{n:.3g} synthetic {L}-nt reads per GPU -> ShortSeq{'64' if L <= 32 else '192'} pack + dedup count "
                     f"({u:.3g} distinct sequences in the generator), BASELINE.json configs[1]",
         "reads_per_gpu": n, "distinct_sequences": u, "read_len": L,
-        "parallelism": f"dp{world}: reads sharded by index, local tables merged by hash-partitioned all-to-all" if world > 1 else "single GPU",
+        "parallelism": (f"dp{world}: reads sharded by index, local tables merged by a hash-partitioned exchange of the uniques "
+                        f"({'NCCL all-to-all' if args.nccl_exchange else 'export kernel stores into the owners over NVLink peer memory'})")
+        if world > 1 else "single GPU",
         "l2_policy": "inputs (>= 40 GB per step) far exceed the 126 MB L2; no flush needed",
     }
 
@@ -263,7 +266,7 @@ def run_ours(args):
     import shortseq_b200 as sq
     from shortseq_b200 import _lib
     from shortseq_b200._runtime import ptr
-    from shortseq_b200.distributed import merge_alltoall
+    from shortseq_b200.distributed import PeerExchange, merge_alltoall, merge_peer
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -281,9 +284,12 @@ def run_ours(args):
     words = ctx.empty((n,) if W == 1 else (n, 3), torch.int64)
     lens = ctx.empty((n,), torch.uint8)
     local = sq.DeviceCounter(klass, expected_unique=u)
-    owner = None
+    owner = exchange = None
     if world > 1:
-        owner = sq.DeviceCounter(klass, expected_unique=2 * u // world, hash_rot=world.bit_length() - 1)
+        # every rank draws from the same u keys, and owners split the key space evenly by hash
+        owner = sq.DeviceCounter(klass, expected_unique=int(1.1 * u / world) + 1024, hash_rot=world.bit_length() - 1)
+        if klass == sq.CLASS_64 and not args.nccl_exchange:
+            exchange = PeerExchange(ctx)
     h = ctx.bind()
     kernel_ms, uniques_seen, phase_ms = [], [0], []
 
@@ -298,7 +304,10 @@ def run_ours(args):
         phase_ms.append(tuple(x.value for x in d))
         if world > 1:
             _lib.check(lib.ssq_counter_clear(owner.handle))
-            merge_alltoall(local, owner=owner)
+            if exchange is not None:
+                merge_peer(local, owner, exchange)        # export kernel stores straight into the owners' memory (NVLink)
+            else:
+                merge_alltoall(local, owner=owner)        # export, then NCCL all-to-all
             uniques_seen[0] = len(owner)
         else:
             uniques_seen[0] = len(local)          # device->host read of the step's result
@@ -392,7 +401,7 @@ def run_ours(args):
         h_words = torch.empty((ne,) if W == 1 else (ne, 3), dtype=torch.int64).pin_memory()
         del eb
         ectr = sq.DeviceCounter(klass, expected_unique=ue)
-        eowner = sq.DeviceCounter(klass, expected_unique=2 * ue // world, hash_rot=world.bit_length() - 1) if world > 1 else None
+        eowner = sq.DeviceCounter(klass, expected_unique=int(1.1 * ue / world) + 1024, hash_rot=world.bit_length() - 1) if world > 1 else None
         rep = _lib.Report()
 
         def estep():
@@ -402,7 +411,10 @@ def run_ours(args):
             assert rep.code == 0
             if world > 1:
                 _lib.check(lib.ssq_counter_clear(eowner.handle))
-                merge_alltoall(ectr, owner=eowner)
+                if exchange is not None:
+                    merge_peer(ectr, eowner, exchange)
+                else:
+                    merge_alltoall(ectr, owner=eowner)
                 return len(eowner)
             return len(ectr)
 
@@ -436,6 +448,8 @@ def run_ours(args):
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if exchange is not None:
+            exchange.close()
         dist.destroy_process_group()
 
 

@@ -69,6 +69,32 @@ class DeviceCounter:
         _lib.check(_lib.lib().ssq_counter_merge(self.handle, ptr(words), ptr(lens), ptr(counts), int(lens.numel())))
         _batch.raise_for_report(self.ctx.sync())
 
+    def clear(self):
+        """Forget every key (the table keeps its size)."""
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_clear(self.handle))
+
+    def merge_raw(self, words_ptr, lens_ptr, counts_ptr, n):
+        """merge() on raw device pointers (the receive buffers of distributed.PeerExchange)."""
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_merge(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), int(n)))
+        _batch.raise_for_report(self.ctx.sync())
+
+    def export_counts(self, n_parts):
+        """Tuples per hash partition (device int64 tensor) without exporting them (ShortSeq64 counters)."""
+        parts = self.ctx.empty((n_parts,), torch.int64)
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_export_counts(self.handle, int(n_parts), ptr(parts)))
+        return parts
+
+    def export_to(self, n_parts, dst_table):
+        """Write partition p's tuples to the device pointers dst_table[0][p] (words), dst_table[1][p] (lens),
+        dst_table[2][p] (counts); dst_table is an int64 device tensor [3, n_parts].  The pointers may be peer memory."""
+        assert dst_table.dtype == torch.int64 and tuple(dst_table.shape) == (3, n_parts) and dst_table.is_contiguous()
+        self.ctx.bind()
+        base = dst_table.data_ptr()
+        _lib.check(_lib.lib().ssq_counter_export_to(self.handle, int(n_parts), base, base + 8 * n_parts, base + 16 * n_parts))
+
     def track_first_index(self, arr, base_index=0):
         """Record the first occurrence index of every key over this packed batch (dict order)."""
         self.ctx.bind()

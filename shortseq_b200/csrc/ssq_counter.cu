@@ -29,6 +29,8 @@ int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *asci
 
 constexpr int kThreads = 256;
 
+static TableView view_of(const ssq_counter *c);
+
 // gate[0] = stop flag, gate[1] = index of the first stopped sub-batch
 __global__ void gate_kernel(u64 *gate, const u64 *size, u64 incoming, u64 limit, u64 batch_index) {
     if (gate[0] == 0 && *size + incoming > limit) { gate[0] = 1; gate[1] = batch_index; }
@@ -410,7 +412,19 @@ count_regions_kernel(TableView t, RegionParts rp) {
         }
     }
     if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
-    block_add_new(t, my_new, s_new);
+    // keys created in this region: table size and the region's occupancy
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+    if (lane == 0) s_new[warp] = my_new;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (u32 k = 0; k < W; k++) tot += s_new[k];
+        if (tot) {
+            atomicAdd(t.size, (u64)tot);
+            red_add_u32(t.region_count + region, tot);
+        }
+    }
 }
 
 // Fallback for tables whose regions exceed shared memory: insert the level-1 partitions in order.  Block b handles
@@ -586,6 +600,113 @@ __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, i
     }
 }
 
+// ---- single-pass export of ShortSeq64 tables ---------------------------------------------------
+// The table is hash-ordered and probing never leaves a region, so hash partition p is exactly the slot range
+// [p * cap / P, (p + 1) * cap / P) and the occupied slots of every region are known (TableView::region_count).
+// An exclusive scan of those counts gives every region its place in the output; one pass over the table then
+// compacts the regions in order -- no counting pass, no atomics, a deterministic order.  With per-partition
+// destination pointers (ssq_counter_export_to) partition p's tuples go straight to dst[p], which may be memory of
+// another GPU (NVLink peer stores): the export IS the send side of the multi-GPU exchange.
+struct ExportDst {
+    u64 *words; uint8_t *lens; u64 *counts; int64_t *first_idx;       // one output array each, or ...
+    u64 *const *pw; uint8_t *const *pl; u64 *const *pc;               // ... device tables of per-partition destinations
+};
+
+__global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, const int64_t *region_base, int log2_parts, ExportDst d) {
+    constexpr int kTile = kThreads * kExportItems;
+    __shared__ u32 s_warp[kThreads / 32];
+    __shared__ u64 s_word[kTile], s_count[kTile];      // the tile's tuples in output order: stores leave coalesced,
+    __shared__ uint8_t s_len[kTile];                   // which is what NVLink peer stores need
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int log2_regions = t.log2_cap - t.log2_region;
+    const u32 nregions = 1u << log2_regions;
+    const u32 R = 1u << t.log2_region;
+    for (u32 region = blockIdx.x; region < nregions; region += gridDim.x) {
+        const int64_t base = region_base[region];
+        if (region_base[region + 1] == base) continue;                  // empty region (CTA-uniform)
+        u64 *W; uint8_t *L; u64 *C;
+        int64_t o = base;
+        if (d.pw != nullptr) {
+            const u32 part = region >> (log2_regions - log2_parts);
+            o = base - region_base[(size_t)part << (log2_regions - log2_parts)];
+            W = d.pw[part]; L = d.pl[part]; C = d.pc[part];
+        } else {
+            W = d.words; L = d.lens; C = d.counts;
+        }
+        const u64 slot0 = (u64)region << t.log2_region;
+        for (u32 tile0 = 0; tile0 < R; tile0 += kTile) {
+            u64 key[kExportItems], cnt[kExportItems];
+            u32 n_used = 0;
+#pragma unroll
+            for (int k = 0; k < kExportItems; k++) {
+                const u32 s = tile0 + k * kThreads + threadIdx.x;
+                key[k] = 0;
+                if (s < R) {
+                    const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(t.slots)[slot0 + s];
+                    key[k] = v.x; cnt[k] = v.y;
+                }
+                n_used += key[k] != 0;
+            }
+            u32 incl = n_used;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if ((int)lane >= dd) incl += x; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            u32 before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; w++) { const u32 x = s_warp[w]; if (w < (int)warp) before += x; total += x; }
+            u32 at = before + incl - n_used;
+#pragma unroll
+            for (int k = 0; k < kExportItems; k++) {
+                if (key[k] == 0) continue;
+                const u64 s = slot0 + tile0 + k * kThreads + threadIdx.x;
+                u32 len;
+                const u64 h2 = slot64_h2(t, s, key[k], len);
+                s_word[at] = unmix64(rotr64(h2, t.rot));
+                s_len[at] = (uint8_t)len;
+                s_count[at] = cnt[k];
+                if (d.first_idx) d.first_idx[o + at] = (int64_t)(t.first_idx ? t.first_idx[s] : kNoIndex);
+                ++at;
+            }
+            __syncthreads();
+            for (u32 i = threadIdx.x; i < total; i += kThreads) {
+                W[o + i] = s_word[i];
+                C[o + i] = s_count[i];
+                L[o + i] = s_len[i];
+            }
+            o += total;
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void export_part_counts_kernel(const int64_t *region_base, int log2_regions, int log2_parts, int64_t *part_counts) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < (1 << log2_parts)) {
+        const int sh = log2_regions - log2_parts;
+        part_counts[p] = region_base[(size_t)(p + 1) << sh] - region_base[(size_t)p << sh];
+    }
+}
+
+// region_base = exclusive scan of the region counts (enqueued on the context's stream)
+static int scan_regions(ssq_counter *c) {
+    const int64_t nregions = (int64_t)1 << (c->log2_cap - region_bits_for(c->log2_cap));
+    if (!c->region_base) SSQ_CUDA(cudaMalloc(&c->region_base, sizeof(int64_t) * (size_t)(nregions + 1)));
+    return scan_u32_counts(c->ctx, c->region_count, nregions, c->region_base);
+}
+
+static bool region_export_ok(const ssq_counter *c, int log2_parts) {
+    return c->klass == SSQ_CLASS_64 && log2_parts <= c->log2_cap - region_bits_for(c->log2_cap);
+}
+
+static int launch_export_regions(ssq_counter *c, int log2_parts, const ExportDst &d) {
+    const int64_t nregions = (int64_t)1 << (c->log2_cap - region_bits_for(c->log2_cap));
+    const int grid = grid_for(c->ctx, nregions, 8);
+    export_regions_kernel<<<grid, kThreads, 0, c->ctx->stream>>>(view_of(c), c->region_base, log2_parts, d);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
 __global__ void fill_u64_kernel(u64 *p, u64 v, u64 n) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -601,6 +722,7 @@ static TableView view_of(const ssq_counter *c) {
     t.log2_cap = c->log2_cap;
     t.rot = c->hash_rot;
     t.log2_region = region_bits_for(c->log2_cap);
+    t.region_count = c->region_count;
     return t;
 }
 
@@ -623,12 +745,19 @@ static int grow(ssq_counter *c, int new_log2) {
         SSQ_CUDA(cudaMalloc(&nfirst, nslots * sizeof(u64)));
         SSQ_CUDA(cudaMemsetAsync(nfirst, 0xFF, nslots * sizeof(u64), st));
     }
+    u32 *nregion = nullptr;
+    const size_t nregions = nslots >> region_bits_for(new_log2);
+    if (c->klass == SSQ_CLASS_64) {
+        SSQ_CUDA(cudaMalloc(&nregion, nregions * sizeof(u32)));
+        SSQ_CUDA(cudaMemsetAsync(nregion, 0, nregions * sizeof(u32), st));
+    }
     TableView src = view_of(c);
     TableView dst = src;
     dst.slots = (u64 *)nslots_p;
     dst.first_idx = nfirst;
     dst.log2_cap = new_log2;
     dst.log2_region = region_bits_for(new_log2);
+    dst.region_count = nregion;
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), st));
     int grid = grid_for(ctx, ((int64_t)1 << c->log2_cap) / kThreads, 8);
     if (c->klass == SSQ_CLASS_64) rehash_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, st>>>(src, dst);
@@ -637,8 +766,12 @@ static int grow(ssq_counter *c, int new_log2) {
     SSQ_CUDA(cudaStreamSynchronize(st));
     SSQ_CUDA(cudaFree(c->slots));
     if (c->first_idx) SSQ_CUDA(cudaFree(c->first_idx));
+    if (c->region_count) SSQ_CUDA(cudaFree(c->region_count));
+    if (c->region_base) SSQ_CUDA(cudaFree(c->region_base));
+    c->region_base = nullptr;
     c->slots = nslots_p;
     c->first_idx = nfirst;
+    c->region_count = nregion;
     c->log2_cap = new_log2;
     return SSQ_OK;
 }
@@ -893,6 +1026,8 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->log2_cap = log2_cap_for(expected_unique);
     c->slots = nullptr;
     c->first_idx = nullptr;
+    c->region_count = nullptr;
+    c->region_base = nullptr;
     c->expected_unique = expected_unique;
     c->part_keys = nullptr;
     c->part_cursor = nullptr;
@@ -912,6 +1047,11 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->h_gate = c->h_size + 1;
     SSQ_CUDA(cudaMemsetAsync(c->slots, 0, bytes, ctx->stream));
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, 4 * sizeof(u64), ctx->stream));
+    if (klass == SSQ_CLASS_64) {
+        const size_t nregions = ((size_t)1 << c->log2_cap) >> region_bits_for(c->log2_cap);
+        SSQ_CUDA(cudaMalloc(&c->region_count, nregions * sizeof(u32)));
+        SSQ_CUDA(cudaMemsetAsync(c->region_count, 0, nregions * sizeof(u32), ctx->stream));
+    }
     *out = c;
     return SSQ_OK;
 }
@@ -922,6 +1062,8 @@ int ssq_counter_destroy(ssq_counter *c) {
     cudaStreamSynchronize(c->ctx->stream);
     cudaFree(c->slots);
     cudaFree(c->first_idx);
+    cudaFree(c->region_count);
+    cudaFree(c->region_base);
     cudaFree(c->part_keys);
     cudaFree(c->part_cursor);
     cudaFree(c->region_keys);
@@ -940,6 +1082,8 @@ int ssq_counter_clear(ssq_counter *c) {
     SSQ_CUDA(cudaMemsetAsync(c->slots, 0, nslots * slot_bytes(c->klass), c->ctx->stream));
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), c->ctx->stream));
     if (c->first_idx) SSQ_CUDA(cudaMemsetAsync(c->first_idx, 0xFF, nslots * sizeof(u64), c->ctx->stream));
+    if (c->region_count)
+        SSQ_CUDA(cudaMemsetAsync(c->region_count, 0, (nslots >> region_bits_for(c->log2_cap)) * sizeof(u32), c->ctx->stream));
     return SSQ_OK;
 }
 
@@ -1093,6 +1237,14 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
     cudaStream_t st = ctx->stream;
     int log2_parts = 0;
     while ((1 << log2_parts) < n_parts) log2_parts++;
+    if (region_export_ok(c, log2_parts)) {                 // ShortSeq64: one pass, region by region
+        int rc = scan_regions(c);
+        if (rc) return rc;
+        export_part_counts_kernel<<<1, kMaxParts, 0, st>>>(c->region_base, c->log2_cap - region_bits_for(c->log2_cap), log2_parts, part_counts);
+        SSQ_LAUNCH_CHECK();
+        ExportDst d{(u64 *)words, lens, (u64 *)counts, first_idx, nullptr, nullptr, nullptr};
+        return launch_export_regions(c, log2_parts, d);
+    }
     u64 *cursors = nullptr;
     {
         void *scratch = nullptr;
@@ -1120,6 +1272,34 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "export kernels", __FILE__, __LINE__);
     return SSQ_OK;
+}
+
+int ssq_counter_export_counts(ssq_counter *c, int n_parts, int64_t *part_counts) {
+    SSQ_ARG(c != nullptr && part_counts != nullptr, "NULL argument");
+    SSQ_ARG(n_parts >= 1 && n_parts <= kMaxParts && (n_parts & (n_parts - 1)) == 0, "n_parts must be a power of two <= 256");
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    if (!region_export_ok(c, log2_parts)) { set_error("ssq_counter_export_counts needs a ShortSeq64 counter with at least n_parts regions"); return SSQ_ERR_ARG; }
+    DeviceGuard g(c->ctx->device);
+    int rc = scan_regions(c);
+    if (rc) return rc;
+    export_part_counts_kernel<<<1, kMaxParts, 0, c->ctx->stream>>>(c->region_base, c->log2_cap - region_bits_for(c->log2_cap), log2_parts, part_counts);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_counter_export_to(ssq_counter *c, int n_parts, uint64_t *const *dst_words, uint8_t *const *dst_lens,
+                          uint64_t *const *dst_counts) {
+    SSQ_ARG(c != nullptr && dst_words != nullptr && dst_lens != nullptr && dst_counts != nullptr, "NULL argument");
+    SSQ_ARG(n_parts >= 1 && n_parts <= kMaxParts && (n_parts & (n_parts - 1)) == 0, "n_parts must be a power of two <= 256");
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    if (!region_export_ok(c, log2_parts)) { set_error("ssq_counter_export_to needs a ShortSeq64 counter with at least n_parts regions"); return SSQ_ERR_ARG; }
+    DeviceGuard g(c->ctx->device);
+    int rc = scan_regions(c);
+    if (rc) return rc;
+    ExportDst d{nullptr, nullptr, nullptr, nullptr, (u64 *const *)dst_words, dst_lens, (u64 *const *)dst_counts};
+    return launch_export_regions(c, log2_parts, d);
 }
 
 }  // extern "C"

@@ -206,4 +206,34 @@ int ssq_memset(ssq_ctx *ctx, void *dst, int value, size_t bytes) {
     return SSQ_OK;
 }
 
+// CUDA IPC: share a cudaMalloc'ed buffer with the other single-GPU processes of the box (multi-GPU exchange over
+// NVLink peer memory).  handle = the 64 bytes of a cudaIpcMemHandle_t.
+int ssq_ipc_get_handle(ssq_ctx *ctx, void *dptr, void *handle64) {
+    SSQ_ARG(ctx != nullptr && dptr != nullptr && handle64 != nullptr, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    SSQ_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, sizeof(h));
+    return SSQ_OK;
+}
+
+int ssq_ipc_open(ssq_ctx *ctx, const void *handle64, void **dptr) {
+    SSQ_ARG(ctx != nullptr && dptr != nullptr && handle64 != nullptr, "NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *dptr = nullptr;
+    SSQ_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SSQ_OK;
+}
+
+int ssq_ipc_close(ssq_ctx *ctx, void *dptr) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    if (!dptr) return SSQ_OK;
+    DeviceGuard g(ctx->device);
+    SSQ_CUDA(cudaIpcCloseMemHandle(dptr));
+    return SSQ_OK;
+}
+
 }  // extern "C"

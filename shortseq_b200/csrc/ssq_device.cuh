@@ -96,6 +96,9 @@ __device__ __forceinline__ void st_release_u64(u64 *p, u64 v) {
 __device__ __forceinline__ void red_add_u64(u64 *p, u64 v) {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_u32(u32 *p, u32 v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_min_u64(u64 *p, u64 v) {
     asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }

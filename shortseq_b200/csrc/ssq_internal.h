@@ -39,6 +39,8 @@ struct ssq_counter {
     int log2_cap;         // capacity = 1 << log2_cap slots
     void *slots;          // class 64: {key, count}[cap] (16 B); class 192: {meta, w0, w1, w2}[cap] (32 B)
     ssq::u64 *first_idx;  // optional side array [cap] (lazily allocated)
+    ssq::u32 *region_count;  // class 64: occupied slots per table region [cap >> region bits]
+    int64_t *region_base;    // class 64: [regions + 1] exclusive scan of region_count (filled by the export)
     ssq::u64 *d_size;     // number of occupied slots (device)
     ssq::u64 *h_size;     // pinned
     ssq::u64 *d_gate;     // {stop flag, first stopped sub-batch} (device, see run_gated)
@@ -109,6 +111,7 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
 // exclusive scan helpers (ssq_scan.cu)
 int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out);
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off);
+int scan_u32_counts(ssq_ctx *ctx, const u32 *counts, int64_t n, int64_t *out /*[n+1]*/);
 int scan_synth_lens(ssq_ctx *ctx, uint64_t seed, int64_t first_read, int64_t n, int64_t n_keys,
                     int32_t len_lo, int32_t len_hi, int64_t *offsets);
 

@@ -16,6 +16,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 struct LenU8 { const uint8_t *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
 struct LenU16 { const uint16_t *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
 struct I64 { const int64_t *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
+struct CountU32 { const u32 *p; __device__ int64_t operator()(int64_t i) const { return p[i]; } };
 // ceil(len/32) words of a ShortSeqVar read (reference util.pyx:29-33); lengths outside
 // 0..1024 contribute 0 words (the pack kernel reports them).
 struct VarWords {
@@ -138,6 +139,10 @@ static int scan_exclusive(ssq_ctx *ctx, F f, int64_t n, int64_t *out /*[n+1]*/) 
 int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out) {
     if (len_bytes == 1) return scan_exclusive(ctx, LenU8{(const uint8_t *)lens}, n, out);
     return scan_exclusive(ctx, LenU16{(const uint16_t *)lens}, n, out);
+}
+
+int scan_u32_counts(ssq_ctx *ctx, const u32 *counts, int64_t n, int64_t *out) {
+    return scan_exclusive(ctx, CountU32{counts}, n, out);
 }
 
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off) {

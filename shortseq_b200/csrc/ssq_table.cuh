@@ -68,6 +68,7 @@ struct TableView {
     int log2_cap;
     int rot;
     int log2_region;  // ShortSeq64 tables: probing wraps inside regions of 2^log2_region slots
+    u32 *region_count;  // ShortSeq64 tables: occupied slots per region (the export derives its offsets from them)
 };
 
 // Regions of 2^12 slots for tables of 2^18 .. 2^28 slots (64 .. 65536 regions); 1/64 of a smaller table; larger
@@ -94,7 +95,12 @@ __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 k
         u64 k = ld_relaxed_u64(p);
         if (k == 0) {
             k = atomicCAS(p, 0ull, key);
-            if (k == 0) { red_add_u64(p + 1, add); is_new = true; return slot; }
+            if (k == 0) {
+                red_add_u64(p + 1, add);
+                red_add_u32(t.region_count + (slot >> t.log2_region), 1u);
+                is_new = true;
+                return slot;
+            }
         }
         if (k == key) { red_add_u64(p + 1, add); return slot; }
         off = (off + 1) & rmask;

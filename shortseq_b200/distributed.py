@@ -83,6 +83,99 @@ def merge_alltoall(local, group=None, owner=None):
     return owner
 
 
+class PeerExchange:
+    """Receive buffers of this rank for the multi-GPU merge, mapped into every other rank of the box through CUDA
+    IPC, so that ssq_counter_export_to on the sending GPU stores the tuples an owner is due straight into the
+    owner's memory over NVLink -- the export kernel is the exchange; NCCL only carries the small size matrix.
+    One object per process, reused across merges (buffers grow collectively when a merge needs more)."""
+
+    def __init__(self, ctx, group=None):
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap = 0
+        self.mine = [0, 0, 0]                       # words / lens / counts receive buffers (device pointers)
+        self.peer = [[0] * self.world for _ in range(3)]
+        self._opened = []
+
+    def _release(self):
+        from . import _lib
+        lib, h = _lib.lib(), self.ctx.bind()
+        for p in self._opened:
+            lib.ssq_ipc_close(h, p)
+        self._opened = []
+        for p in self.mine:
+            if p:
+                lib.ssq_free(h, p)
+        self.mine = [0, 0, 0]
+        self.cap = 0
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free this rank's."""
+        torch.cuda.synchronize(self.ctx.device)
+        dist.barrier(self.group)
+        self._release()
+
+    def ensure(self, need):
+        """Collective (every rank passes the same `need`): receive buffers for at least `need` tuples."""
+        if need <= self.cap:
+            return
+        import ctypes as C
+        from . import _lib
+        lib, h = _lib.lib(), self.ctx.bind()
+        torch.cuda.synchronize(self.ctx.device)
+        dist.barrier(self.group)                   # nobody is still writing into, or reading from, the old buffers
+        self._release()
+        cap = int(need * 1.25) + 1024
+        handles = torch.zeros(3 * 64, dtype=torch.uint8)
+        for k, elem in enumerate((8, 1, 8)):
+            p = C.c_void_p()
+            _lib.check(lib.ssq_malloc(h, cap * elem, C.byref(p)))
+            self.mine[k] = p.value
+            hb = (C.c_ubyte * 64)()
+            _lib.check(lib.ssq_ipc_get_handle(h, p, hb))
+            handles[64 * k: 64 * (k + 1)] = torch.frombuffer(bytes(hb), dtype=torch.uint8)
+        mine = handles.to(self.ctx.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        for r in range(self.world):
+            hr = gathered[r].cpu().numpy().tobytes()
+            for k in range(3):
+                if r == self.rank:
+                    self.peer[k][r] = self.mine[k]
+                else:
+                    p = C.c_void_p()
+                    _lib.check(lib.ssq_ipc_open(h, hr[64 * k: 64 * (k + 1)], C.byref(p)))
+                    self.peer[k][r] = p.value
+                    self._opened.append(p.value)
+        self.cap = cap
+
+
+def merge_peer(local, owner, exchange, group=None):
+    """merge_alltoall with the exchange fused into the export: every rank's export kernel writes each owner's share
+    directly into that owner's receive buffer (NVLink peer stores through `exchange`, a PeerExchange).  ShortSeq64
+    counters; `owner` must have been created with hash_rot = log2(world).  Returns `owner`."""
+    world, rank = exchange.world, exchange.rank
+    t0 = _tick("start", time.perf_counter(), local.ctx) if _TIMING else 0.0
+    parts = local.export_counts(world)                                  # tuples this rank holds for every owner
+    matrix = [torch.empty_like(parts) for _ in range(world)]
+    dist.all_gather(matrix, parts, group=group)                         # matrix[src][dst]
+    m = torch.stack(matrix).cpu().numpy()                               # host sync: every rank has entered this merge
+    t0 = _tick("size matrix", t0, local.ctx)
+    exchange.ensure(int(m.sum(axis=0).max()))
+    import numpy as np
+    before = m[:rank].sum(axis=0) if rank else np.zeros(world, dtype=np.int64)   # where my block starts in each owner's buffer
+    table = np.empty((3, world), dtype=np.int64)
+    for k, elem in enumerate((8, 1, 8)):
+        table[k] = [exchange.peer[k][d] + elem * int(before[d]) for d in range(world)]
+    local.export_to(world, torch.from_numpy(table).to(local.ctx.device))
+    torch.cuda.synchronize(local.ctx.device)                            # my stores have landed ...
+    dist.barrier(group)                                                 # ... and so have everyone else's
+    t0 = _tick("export = exchange (peer stores)", t0, local.ctx)
+    owner.merge_raw(exchange.mine[0], exchange.mine[1], exchange.mine[2], int(m[:, rank].sum()))
+    _tick("merge into owner table", t0, local.ctx)
+    return owner
+
+
 def global_size(owner, group=None):
     """Number of distinct keys over all ranks (sum of the disjoint owner tables)."""
     t = torch.tensor([len(owner)], dtype=torch.int64, device=owner.ctx.device)

@@ -15,10 +15,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, klass, out_dir):
+def _worker(rank, world, port, klass, out_dir, peer=False):
     import torch.distributed as dist
     import shortseq_b200 as sq
-    from shortseq_b200.distributed import global_size, merge_alltoall
+    from shortseq_b200.distributed import PeerExchange, global_size, merge_alltoall, merge_peer
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -27,7 +27,15 @@ def _worker(rank, world, port, klass, out_dir):
         b = sq.synth_reads(300_000, 40_000, lo, hi, seed=0x5EED0001, first_read=rank * 300_000)
         local = sq.DeviceCounter(klass, expected_unique=50_000)
         local.pack_count(b)
-        owner = merge_alltoall(local)
+        if peer:
+            ex = PeerExchange(local.ctx)
+            owner = sq.DeviceCounter(klass, expected_unique=40_000, hash_rot=world.bit_length() - 1)
+            for _ in range(2):                      # twice: buffers are reused, the owner table is cleared in between
+                owner.clear()
+                merge_peer(local, owner, ex)
+            ex.close()
+        else:
+            owner = merge_alltoall(local)
         total = global_size(owner)
         keys, counts, _, _ = owner.export(1)
         w, l, _ = keys.to_host()
@@ -36,14 +44,15 @@ def _worker(rank, world, port, klass, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("klass", [0, 1])
-def test_multi_gpu_merge_matches_oracle(tmp_path, klass, oracle):
+@pytest.mark.parametrize("klass,peer", [(0, False), (1, False), (0, True)])
+def test_multi_gpu_merge_matches_oracle(tmp_path, klass, peer, oracle):
+    """peer=True: the export kernel stores each owner's tuples straight into that owner's memory (CUDA IPC + NVLink)."""
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from shortseq_b200 import hashing
-    mp.spawn(_worker, args=(world, _free_port(), klass, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), klass, str(tmp_path), peer), nprocs=world, join=True)
     lo, hi = (18, 32) if klass == 0 else (40, 96)
     buf, off = oracle.synth_reads(0x5EED0001, 0, 600_000, 40_000, lo, hi)
     ow, ol, _ = oracle.pack_batch(klass, buf, off)
