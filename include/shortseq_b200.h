@@ -190,10 +190,12 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
 /* Multi-GPU send side without an intermediate buffer (ShortSeq64 counters): part_counts[n_parts] (device) = tuples
  * per hash partition; then partition p's tuples are written to dst_words[p][0..], dst_lens[p][0..], dst_counts[p][0..]
  * -- device arrays of n_parts DEVICE pointers, each of which may point into another GPU's memory (opened with
- * ssq_ipc_open): the export kernel stores over NVLink, no collective call moves the data. */
+ * ssq_ipc_open): the export kernel stores over NVLink, no collective call moves the data.  The kernel walks the
+ * partitions cyclically starting at first_part: rank r of P passes (r + 1) % P so that at any moment every owner
+ * receives from one sender instead of all senders converging on owner 0, then owner 1, ... */
 int ssq_counter_export_counts(ssq_counter *c, int n_parts, int64_t *part_counts);
-int ssq_counter_export_to(ssq_counter *c, int n_parts, uint64_t *const *dst_words, uint8_t *const *dst_lens,
-                          uint64_t *const *dst_counts);
+int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t *const *dst_words,
+                          uint8_t *const *dst_lens, uint64_t *const *dst_counts);
 /* CUDA IPC for the peer exchange: handle64 = 64 opaque bytes to pass to the other single-GPU processes of the box. */
 int ssq_ipc_get_handle(ssq_ctx *ctx, void *dptr, void *handle64);
 int ssq_ipc_open(ssq_ctx *ctx, const void *handle64, void **dptr);

@@ -87,13 +87,15 @@ class DeviceCounter:
         _lib.check(_lib.lib().ssq_counter_export_counts(self.handle, int(n_parts), ptr(parts)))
         return parts
 
-    def export_to(self, n_parts, dst_table):
+    def export_to(self, n_parts, dst_table, first_part=0):
         """Write partition p's tuples to the device pointers dst_table[0][p] (words), dst_table[1][p] (lens),
-        dst_table[2][p] (counts); dst_table is an int64 device tensor [3, n_parts].  The pointers may be peer memory."""
+        dst_table[2][p] (counts); dst_table is an int64 device tensor [3, n_parts].  The pointers may be peer memory;
+        the kernel walks the partitions cyclically from first_part (stagger it across ranks)."""
         assert dst_table.dtype == torch.int64 and tuple(dst_table.shape) == (3, n_parts) and dst_table.is_contiguous()
         self.ctx.bind()
         base = dst_table.data_ptr()
-        _lib.check(_lib.lib().ssq_counter_export_to(self.handle, int(n_parts), base, base + 8 * n_parts, base + 16 * n_parts))
+        _lib.check(_lib.lib().ssq_counter_export_to(self.handle, int(n_parts), int(first_part), base, base + 8 * n_parts,
+                                                   base + 16 * n_parts))
 
     def track_first_index(self, arr, base_index=0):
         """Record the first occurrence index of every key over this packed batch (dict order)."""

@@ -612,16 +612,20 @@ struct ExportDst {
     u64 *const *pw; uint8_t *const *pl; u64 *const *pc;               // ... device tables of per-partition destinations
 };
 
-__global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, const int64_t *region_base, int log2_parts, ExportDst d) {
+__global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, const int64_t *region_base, int log2_parts, u32 first_region,
+                                                                  ExportDst d) {
     constexpr int kTile = kThreads * kExportItems;
     __shared__ u32 s_warp[kThreads / 32];
-    __shared__ u64 s_word[kTile], s_count[kTile];      // the tile's tuples in output order: stores leave coalesced,
-    __shared__ uint8_t s_len[kTile];                   // which is what NVLink peer stores need
+    // The tile's tuples are staged in output order, shifted so that a staged element and its destination have the same
+    // 16-byte phase: the bulk of a tile then leaves as coalesced 16-byte stores (what NVLink peer stores need).
+    __shared__ __align__(16) u64 s_word[kTile + 2], s_count[kTile + 2];
+    __shared__ __align__(16) uint8_t s_len[kTile + 16];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int log2_regions = t.log2_cap - t.log2_region;
     const u32 nregions = 1u << log2_regions;
     const u32 R = 1u << t.log2_region;
-    for (u32 region = blockIdx.x; region < nregions; region += gridDim.x) {
+    for (u32 ri = blockIdx.x; ri < nregions; ri += gridDim.x) {
+        const u32 region = (ri + first_region) & (nregions - 1);       // the walk starts at first_region and wraps around
         const int64_t base = region_base[region];
         if (region_base[region + 1] == base) continue;                  // empty region (CTA-uniform)
         u64 *W; uint8_t *L; u64 *C;
@@ -655,6 +659,10 @@ __global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, c
             u32 before = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; w++) { const u32 x = s_warp[w]; if (w < (int)warp) before += x; total += x; }
+            // element i of the tile goes to index o + i: stage it at i + phase so that both share alignment
+            const u32 ph8 = (u32)((reinterpret_cast<uintptr_t>(W + o) >> 3) & 1);        // u64 arrays: phase within 16 bytes
+            const u32 phc = (u32)((reinterpret_cast<uintptr_t>(C + o) >> 3) & 1);
+            const u32 ph1 = (u32)(reinterpret_cast<uintptr_t>(L + o) & 15);              // byte array
             u32 at = before + incl - n_used;
 #pragma unroll
             for (int k = 0; k < kExportItems; k++) {
@@ -662,17 +670,32 @@ __global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, c
                 const u64 s = slot0 + tile0 + k * kThreads + threadIdx.x;
                 u32 len;
                 const u64 h2 = slot64_h2(t, s, key[k], len);
-                s_word[at] = unmix64(rotr64(h2, t.rot));
-                s_len[at] = (uint8_t)len;
-                s_count[at] = cnt[k];
+                s_word[at + ph8] = unmix64(rotr64(h2, t.rot));
+                s_count[at + phc] = cnt[k];
+                s_len[at + ph1] = (uint8_t)len;
                 if (d.first_idx) d.first_idx[o + at] = (int64_t)(t.first_idx ? t.first_idx[s] : kNoIndex);
                 ++at;
             }
             __syncthreads();
-            for (u32 i = threadIdx.x; i < total; i += kThreads) {
-                W[o + i] = s_word[i];
-                C[o + i] = s_count[i];
-                L[o + i] = s_len[i];
+            {   // u64 arrays: staged span [ph, ph + total); whole 16-byte pairs in the middle, single elements at the ends
+                for (int a = 0; a < 2; a++) {
+                    const u32 ph = a ? phc : ph8;
+                    u64 *dst = (a ? C : W) + o - ph;                    // staged index j <-> dst[j]; dst is 16-byte aligned
+                    const u64 *src = a ? s_count : s_word;
+                    const u32 lo = ph, hi = ph + total;
+                    const u32 mid_lo = (lo + 1) & ~1u, mid_hi = hi & ~1u;
+                    if (threadIdx.x == 0 && lo < mid_lo && lo < hi) dst[lo] = src[lo];
+                    if (threadIdx.x == 1 && mid_hi < hi && mid_hi >= mid_lo) dst[mid_hi] = src[mid_hi];
+                    for (u32 j = mid_lo + 2 * threadIdx.x; j + 2 <= mid_hi; j += 2 * kThreads)
+                        *reinterpret_cast<ulonglong2 *>(dst + j) = *reinterpret_cast<const ulonglong2 *>(src + j);
+                }
+                uint8_t *Lb = L + o - ph1;                              // 16-byte aligned
+                const u32 blo = ph1, bhi = ph1 + total;
+                const u32 bmid_lo = min((blo + 15) & ~15u, bhi), bmid_hi = max(bhi & ~15u, bmid_lo);
+                for (u32 j = blo + threadIdx.x; j < bmid_lo; j += kThreads) Lb[j] = s_len[j];
+                for (u32 j = bmid_hi + threadIdx.x; j < bhi; j += kThreads) Lb[j] = s_len[j];
+                for (u32 j = bmid_lo + 16 * threadIdx.x; j + 16 <= bmid_hi; j += 16 * kThreads)
+                    *reinterpret_cast<uint4 *>(Lb + j) = *reinterpret_cast<const uint4 *>(s_len + j);
             }
             o += total;
             __syncthreads();
@@ -699,10 +722,11 @@ static bool region_export_ok(const ssq_counter *c, int log2_parts) {
     return c->klass == SSQ_CLASS_64 && log2_parts <= c->log2_cap - region_bits_for(c->log2_cap);
 }
 
-static int launch_export_regions(ssq_counter *c, int log2_parts, const ExportDst &d) {
+static int launch_export_regions(ssq_counter *c, int log2_parts, int first_part, const ExportDst &d) {
     const int64_t nregions = (int64_t)1 << (c->log2_cap - region_bits_for(c->log2_cap));
     const int grid = grid_for(c->ctx, nregions, 8);
-    export_regions_kernel<<<grid, kThreads, 0, c->ctx->stream>>>(view_of(c), c->region_base, log2_parts, d);
+    const u32 first_region = (u32)(((int64_t)first_part * nregions) >> log2_parts);
+    export_regions_kernel<<<grid, kThreads, 0, c->ctx->stream>>>(view_of(c), c->region_base, log2_parts, first_region, d);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -1243,7 +1267,7 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
         export_part_counts_kernel<<<1, kMaxParts, 0, st>>>(c->region_base, c->log2_cap - region_bits_for(c->log2_cap), log2_parts, part_counts);
         SSQ_LAUNCH_CHECK();
         ExportDst d{(u64 *)words, lens, (u64 *)counts, first_idx, nullptr, nullptr, nullptr};
-        return launch_export_regions(c, log2_parts, d);
+        return launch_export_regions(c, log2_parts, 0, d);
     }
     u64 *cursors = nullptr;
     {
@@ -1288,10 +1312,11 @@ int ssq_counter_export_counts(ssq_counter *c, int n_parts, int64_t *part_counts)
     return SSQ_OK;
 }
 
-int ssq_counter_export_to(ssq_counter *c, int n_parts, uint64_t *const *dst_words, uint8_t *const *dst_lens,
+int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t *const *dst_words, uint8_t *const *dst_lens,
                           uint64_t *const *dst_counts) {
     SSQ_ARG(c != nullptr && dst_words != nullptr && dst_lens != nullptr && dst_counts != nullptr, "NULL argument");
     SSQ_ARG(n_parts >= 1 && n_parts <= kMaxParts && (n_parts & (n_parts - 1)) == 0, "n_parts must be a power of two <= 256");
+    SSQ_ARG(first_part >= 0 && first_part < n_parts, "first_part out of range");
     int log2_parts = 0;
     while ((1 << log2_parts) < n_parts) log2_parts++;
     if (!region_export_ok(c, log2_parts)) { set_error("ssq_counter_export_to needs a ShortSeq64 counter with at least n_parts regions"); return SSQ_ERR_ARG; }
@@ -1299,7 +1324,7 @@ int ssq_counter_export_to(ssq_counter *c, int n_parts, uint64_t *const *dst_word
     int rc = scan_regions(c);
     if (rc) return rc;
     ExportDst d{nullptr, nullptr, nullptr, nullptr, (u64 *const *)dst_words, dst_lens, (u64 *const *)dst_counts};
-    return launch_export_regions(c, log2_parts, d);
+    return launch_export_regions(c, log2_parts, first_part, d);
 }
 
 }  // extern "C"

@@ -167,7 +167,8 @@ def merge_peer(local, owner, exchange, group=None):
     table = np.empty((3, world), dtype=np.int64)
     for k, elem in enumerate((8, 1, 8)):
         table[k] = [exchange.peer[k][d] + elem * int(before[d]) for d in range(world)]
-    local.export_to(world, torch.from_numpy(table).to(local.ctx.device))
+    # rank r starts with owner r + 1: at any moment every owner receives from one sender
+    local.export_to(world, torch.from_numpy(table).to(local.ctx.device), first_part=(rank + 1) % world)
     torch.cuda.synchronize(local.ctx.device)                            # my stores have landed ...
     dist.barrier(group)                                                 # ... and so have everyone else's
     t0 = _tick("export = exchange (peer stores)", t0, local.ctx)
