@@ -458,6 +458,41 @@ __global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, Part
     block_add_new(t, my_new, s_new);
 }
 
+// ShortSeq192: the records of the level-1 partitions are inserted in partition order (table range of cap/256 slots =
+// 1/256 of the table stays in L2); block b handles the segment scatter CTA (b % num_ctas) filled for partition
+// (b / num_ctas).  A record is {w0, w1, w2, meta}, see meta192_of.
+// The last num_ctas blocks insert the scatter CTAs' overflow segments (unordered, a fraction of a percent of the reads).
+__global__ void __launch_bounds__(kThreads) count_parts192_kernel(TableView t, PartView pv) {
+    __shared__ u32 s_new[kThreads / 32];
+    const u32 p = blockIdx.x / pv.num_ctas;
+    const u32 c = blockIdx.x - p * pv.num_ctas;
+    const size_t seg = (size_t)c * kParts + p;
+    const bool overflow_seg = p >= (u32)kParts;
+    const u32 cnt = overflow_seg ? pv.ovf_count[c] : pv.seg_count[seg];
+    const ulonglong2 *recs = reinterpret_cast<const ulonglong2 *>(overflow_seg ? pv.ovf + (size_t)c * pv.ovf_cap * 4
+                                                                               : pv.keys + seg * pv.seg_cap * 4);
+    const u64 drop = l2_policy_evict_first();
+    u32 my_new = 0;
+    constexpr int kRecs = 2;     // records per thread per round
+    for (u32 i0 = 0; i0 < cnt; i0 += kThreads * kRecs) {
+        ulonglong2 a[kRecs], b[kRecs];
+#pragma unroll
+        for (int j = 0; j < kRecs; j++) {
+            const u32 i = i0 + j * kThreads + threadIdx.x;
+            b[j].y = 0;
+            if (i < cnt) { a[j] = ld_hint_v2u64(recs + 2 * (size_t)i, drop); b[j] = ld_hint_v2u64(recs + 2 * (size_t)i + 1, drop); }
+        }
+#pragma unroll
+        for (int j = 0; j < kRecs; j++) {
+            if (i0 + j * kThreads + threadIdx.x >= cnt) continue;
+            bool is_new = false;
+            insert192_hashed(t, b[j].y & ~0xFFull, a[j].x, a[j].y, b[j].x, (u32)(b[j].y & 0xFF) + 32, 1ull, is_new);
+            my_new += is_new ? 1u : 0u;
+        }
+    }
+    block_add_new(t, my_new, s_new);
+}
+
 // ---- export ---------------------------------------------------------------------------------
 constexpr int kExportItems = 8;    // slots per thread
 constexpr int kMaxParts = 256;
@@ -837,13 +872,13 @@ static int run_gated(ssq_counter *c, int64_t n, Launch launch) {
 constexpr size_t kDirectTableBytes = (size_t)48 << 20;
 
 static bool use_deferred(const ssq_counter *c, int64_t n) {
-    if (c->klass != SSQ_CLASS_64 || c->expected_unique <= 0) return false;
-    const size_t table_bytes = ((size_t)1 << c->log2_cap) * 16;
+    if (c->expected_unique <= 0) return false;
+    const size_t table_bytes = ((size_t)1 << c->log2_cap) * slot_bytes(c->klass);
     // worthwhile when the table cannot live in L2 and the pass brings at least ~1 key per 4 slots
     return table_bytes > kDirectTableBytes && n >= ((int64_t)1 << c->log2_cap) / 4;
 }
 
-int scatter_grid(ssq_ctx *ctx, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
+int scatter_grid(ssq_ctx *ctx, int klass, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
 
 // development tunables (read once per process)
 static int env_int(const char *name, int dflt, int lo, int hi) {
@@ -855,11 +890,16 @@ static int env_int(const char *name, int dflt, int lo, int hi) {
 // Size the level-1 partition buffers for a pass of n keys scattered by `grid` persistent CTAs.
 static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     ssq_ctx *ctx = c->ctx;
+    const int rw = c->klass == SSQ_CLASS_64 ? 1 : 4;        // 64-bit words per record
+    const int line = kLineKeys / rw;                        // records per 128-byte line
     // a CTA sees ~n/grid keys, 1/256 of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
     int64_t per = n / ((int64_t)grid * kParts);
     per = per + per / 16 + 64;
-    per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
-    const int64_t need = per * grid * kParts;
+    per = (per + line - 1) & ~(int64_t)(line - 1);
+    // ShortSeq192 overflow segments: 2 % of a CTA's reads + slack
+    const int64_t ovf_cap = c->klass == SSQ_CLASS_64 ? 0 : n / grid / 50 + 256;
+    const int64_t main_entries = per * grid * kParts * rw;
+    const int64_t need = main_entries + ovf_cap * grid * rw;
     if (need > c->part_cap) {
         SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
         if (c->part_keys) SSQ_CUDA(cudaFree(c->part_keys));
@@ -873,16 +913,20 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
         if (c->part_cursor) SSQ_CUDA(cudaFree(c->part_cursor));
         c->part_cursor = nullptr;
         c->part_ctas = 0;
-        SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * (size_t)grid * kParts));
+        SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * (size_t)grid * (kParts + 1)));
         c->part_ctas = grid;
     }
     pv->keys = c->part_keys;
     pv->seg_count = c->part_cursor;
     pv->seg_cap = (u32)per;
     pv->num_ctas = (u32)grid;
+    pv->ovf = c->part_keys + main_entries;
+    pv->ovf_count = c->part_cursor + (size_t)grid * kParts;
+    pv->ovf_cap = (u32)ovf_cap;
     // a tile brings 512 keys = 2 per partition on average and a ring holds 32: flushing every 4th tile keeps ring
     // overflow (handled, but slow) below one key in a thousand tiles
-    pv->flush_every = (u32)env_int("SSQ_FLUSH_EVERY", 4, 1, 8);
+    // (ShortSeq192 rings hold 8 records: flush after every tile)
+    pv->flush_every = c->klass == SSQ_CLASS_64 ? (u32)env_int("SSQ_FLUSH_EVERY", 4, 1, 8) : 1u;
     return SSQ_OK;
 }
 
@@ -1010,14 +1054,20 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
     if (use_deferred(c, n)) {
         c->last_pass_phases = 2;
         PartView pv;
-        int sgrid = scatter_grid(ctx, n);
+        int sgrid = scatter_grid(ctx, c->klass, n);
         if ((int64_t)sgrid * 65536 > n) sgrid = (int)(n / 65536 > 0 ? n / 65536 : 1);   // keep the segments from being mostly padding
         rc = prepare_parts(c, n, sgrid, &pv);
         if (rc) return rc;
         rc = launch_pack_count(ctx, c->klass, true, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c), pv, nullptr);
         if (rc) return rc;
         SSQ_CUDA(cudaEventRecord(c->ev[1], ctx->stream));
-        rc = launch_count_parts(c, n, pv, c->ev[2]);
+        if (c->klass == SSQ_CLASS_64) {
+            rc = launch_count_parts(c, n, pv, c->ev[2]);
+        } else {
+            SSQ_CUDA(cudaEventRecord(c->ev[2], ctx->stream));
+            count_parts192_kernel<<<(kParts + 1) * pv.num_ctas, kThreads, 0, ctx->stream>>>(view_of(c), pv);
+            SSQ_LAUNCH_CHECK();
+        }
     } else {
         c->last_pass_phases = 1;
         rc = launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets, n, index_base, words, lens, view_of(c),
@@ -1120,7 +1170,7 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
     if (c->expected_unique > 0) {
         int rc = SSQ_OK;
-        if (counts == nullptr && use_deferred(c, n)) {
+        if (counts == nullptr && c->klass == SSQ_CLASS_64 && use_deferred(c, n)) {
             PartView pv;
             int grid = grid_for(ctx, (n + 65535) / 65536, 3);
             rc = prepare_parts(c, n, grid, &pv);

@@ -81,6 +81,10 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// one 32-byte load (sm_100 LDG.256) of a 32-byte aligned slot; not an atomic snapshot as far as the memory model goes
+__device__ __forceinline__ void ld_relaxed_v4u64(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.relaxed.gpu.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
 __device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

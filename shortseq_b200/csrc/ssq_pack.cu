@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     constexpr int W = KLASS == SSQ_CLASS_64 ? 1 : 3;
     constexpr int PAD = 2 * W + 1;
     constexpr int MAX_CHUNKS = (kTileReads * MAXLEN + 30) / 16 + 1;
-    static_assert(MODE != kModeScatter || KLASS == SSQ_CLASS_64, "partition scatter is implemented for ShortSeq64 keys");
+    constexpr int RW = KLASS == SSQ_CLASS_64 ? 1 : 4;     // 64-bit words per staged record (table key / {w0, w1, w2, meta})
     __shared__ u32 codes[MAX_CHUNKS + PAD];
     __shared__ u32 srel[kTileReads + 1];                // read starts relative to the tile start
     __shared__ u32 s_new[kPackThreads / 32];
@@ -200,14 +200,14 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
-    __shared__ u32 s_unstaged_new;
+    __shared__ u32 s_unstaged_new, s_ovf_n;
     const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
-    u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
+    u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap * RW : nullptr;
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;
     if (MODE == kModeScatter) {                      // ordered by the first tile's barrier
         stager_init(stg);
-        if (threadIdx.x == 0) s_unstaged_new = 0;
+        if (threadIdx.x == 0) { s_unstaged_new = 0; s_ovf_n = 0; }
     }
 
     u32 my_new = 0;
@@ -302,13 +302,24 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                 }
                 if constexpr (MODE == kModeScatter) {
                     if (ok) {
-                        // stage the table key for its hash partition
-                        const u64 h2 = rotl64(mix64(w[0]), t.rot);
-                        const u64 key = key64_of(h2, (u32)len);
-                        if (!stage_key(stg, (u32)(h2 >> 56), key)) {   // staging ring full: count it right away
-                            bool is_new = false;
-                            insert64_hashed(t, h2, key, 1ull, is_new);
-                            my_new += is_new ? 1u : 0u;
+                        // stage the table key / record for its hash partition; a full staging ring: count it right away
+                        if constexpr (KLASS == SSQ_CLASS_64) {
+                            const u64 h2 = rotl64(mix64(w[0]), t.rot);
+                            const u64 key = key64_of(h2, (u32)len);
+                            if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
+                        } else {
+                            const u64 h2 = rotl64(hash192(w[0], w[1], w[2], (u32)len), t.rot);
+                            const u64 meta = meta192_of(h2, (u32)len);
+                            if (!stage_rec192(stg, (u32)(h2 >> 56), w[0], w[1], w[2], meta)) {
+                                const u32 pos = atomicAdd(&s_ovf_n, 1u);         // ring full: park the record in the overflow segment
+                                if (pos < pv.ovf_cap) {
+                                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(pv.ovf + ((size_t)blockIdx.x * pv.ovf_cap + pos) * 4);
+                                    dst[0] = make_ulonglong2(w[0], w[1]);
+                                    dst[1] = make_ulonglong2(w[2], meta);
+                                } else {
+                                    insert192_slow(t, h2, w[0], w[1], w[2], (u32)len, &s_unstaged_new);
+                                }
+                            }
                         }
                     }
                 }
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                 if (++since_flush >= pv.flush_every) {
                     since_flush = 0;
                     __syncthreads();
-                    flush_lines<false>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                    flush_lines<false, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
                 }
             }
         }
@@ -327,11 +338,14 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
         cur = nxt; cur_ok = nxt_ok; geom = ngeom; prefetched = nprefetched; nxt = nxt2;
     }
     if constexpr (MODE == kModeScatter) {
-        flush_lines<true>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);   // the loop ended with a barrier
+        flush_lines<true, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);   // the loop ended with a barrier
         __syncthreads();
         for (int p = threadIdx.x; p < kParts; p += kPackThreads)
             pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
-        if (threadIdx.x == 0) my_new += s_unstaged_new;
+        if (threadIdx.x == 0) {
+            my_new += s_unstaged_new;
+            if (KLASS != SSQ_CLASS_64) pv.ovf_count[blockIdx.x] = min(s_ovf_n, pv.ovf_cap);
+        }
     }
     if (MODE != kModePack) {
         // one size update per CTA: a single global counter cannot take one atomic per warp
@@ -445,7 +459,9 @@ static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, con
 }
 
 // grid of the scatter-mode launch for n reads: it fixes the segment layout of the partition buffers
-int scatter_grid(ssq_ctx *ctx, int64_t n) { return fixed_grid<SSQ_CLASS_64, kModeScatter>(ctx, n); }
+int scatter_grid(ssq_ctx *ctx, int klass, int64_t n) {
+    return klass == SSQ_CLASS_64 ? fixed_grid<SSQ_CLASS_64, kModeScatter>(ctx, n) : fixed_grid<SSQ_CLASS_192, kModeScatter>(ctx, n);
+}
 
 // used by ssq_counter.cu: fused pack + (direct insert | partition scatter)
 int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *ascii, int64_t lo, int64_t hi,
@@ -455,7 +471,8 @@ int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *asci
     if (klass == SSQ_CLASS_64)
         return scatter ? launch_fixed<SSQ_CLASS_64, kModeScatter>(ctx, a, t, pv, stop, (int)pv.num_ctas)
                        : launch_fixed<SSQ_CLASS_64, kModeDirect>(ctx, a, t, pv, stop);
-    return launch_fixed<SSQ_CLASS_192, kModeDirect>(ctx, a, t, pv, stop);
+    return scatter ? launch_fixed<SSQ_CLASS_192, kModeScatter>(ctx, a, t, pv, stop, (int)pv.num_ctas)
+                   : launch_fixed<SSQ_CLASS_192, kModeDirect>(ctx, a, t, pv, stop);
 }
 
 }  // namespace ssq

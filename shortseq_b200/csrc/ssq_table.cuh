@@ -48,6 +48,11 @@ struct PartView {
     u32 seg_cap;        // entries per segment (multiple of kLineKeys); keys beyond it are inserted directly by the scatter pass
     u32 num_ctas;       // grid size of the scatter pass
     u32 flush_every;    // fused pack+scatter: tiles between two flushes of the staging rings
+    // ShortSeq192: records that find their staging ring full are appended to the CTA's overflow segment (one scattered
+    // 32-byte store instead of a latency-bound global insert inside the pack loop) and inserted after the partitions
+    u64 *ovf;           // [num_ctas][ovf_cap][4]
+    u32 *ovf_count;     // [num_ctas]
+    u32 ovf_cap;        // records per CTA
 };
 // Level-2 buffers: CTA (p, s) of the second scatter -- slice s of level-1 partition p -- owns the segments
 // keys[((p * slices + s) * kParts + r) * seg_cap ...] of the level-2 partitions r (hash bits 55..48) of partition p.
@@ -142,20 +147,27 @@ __device__ __forceinline__ u64 slot64_h2(const TableView &t, u64 slot, u64 key, 
 // ---- ShortSeq192 -----------------------------------------------------------
 constexpr u64 kLocked = 0xFFull;
 
-__device__ __forceinline__ u64 insert192(const TableView &t, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
+// h2 = rotl(hash192(w0, w1, w2, len), rot); only its top log2(cap) bits are used
+__device__ __forceinline__ u64 insert192_hashed(const TableView &t, u64 h2, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
     const u64 mask = (1ull << t.log2_cap) - 1;
     const u64 state = (u64)(len - 32);
-    u64 slot = rotl64(hash192(w0, w1, w2, len), t.rot) >> (64 - t.log2_cap);
+    u64 slot = h2 >> (64 - t.log2_cap);
     is_new = false;
     u64 probes = 0;
     const u64 limit = 1ull << t.log2_cap;
     while (probes < limit) {
         u64 *p = t.slots + 4 * slot;
-        u64 meta = ld_acquire_u64(p);
+        // The whole slot in one 32-byte load.  A full match is conclusive (words are written once, before the state is
+        // released); anything else that could be a torn view is confirmed with ordered loads below.
+        u64 meta, a0, a1, a2;
+        ld_relaxed_v4u64(p, meta, a0, a1, a2);
         u64 st = meta & 0xFF;
+        if (st == state && a0 == w0 && a1 == w1 && a2 == w2) {
+            red_add_u64(p, add << 8);
+            return slot;
+        }
         if (st == 0) {
-            u64 old = atomicCAS(p, 0ull, kLocked);
-            if (old == 0) {
+            if (atomicCAS(p, 0ull, kLocked) == 0) {
                 st_relaxed_u64(p + 1, w0);
                 st_relaxed_u64(p + 2, w1);
                 st_relaxed_u64(p + 3, w2);
@@ -163,13 +175,19 @@ __device__ __forceinline__ u64 insert192(const TableView &t, u64 w0, u64 w1, u64
                 is_new = true;
                 return slot;
             }
-            st = old & 0xFF;
+            continue;                                      // somebody else took the slot: look again
         }
         if (st == kLocked) continue;                       // being written: look again
-        if (st == state && ld_relaxed_u64(p + 1) == w0 && ld_relaxed_u64(p + 2) == w1 &&
-            ld_relaxed_u64(p + 3) == w2) {
-            red_add_u64(p, add << 8);
-            return slot;
+        // Same length but the words differed.  Words change exactly once, from 0 to their final value, so a word that
+        // is non-zero and different settles it; only a view whose differing words are all still 0 could be torn.
+        const bool settled = (a0 != w0 && a0 != 0) || (a1 != w1 && a1 != 0) || (a2 != w2 && a2 != 0);
+        if (st == state && !settled) {
+            const u64 m2 = ld_acquire_u64(p);
+            if ((m2 & 0xFF) == state && ld_relaxed_u64(p + 1) == w0 && ld_relaxed_u64(p + 2) == w1 &&
+                ld_relaxed_u64(p + 3) == w2) {
+                red_add_u64(p, add << 8);
+                return slot;
+            }
         }
         slot = (slot + 1) & mask;
         ++probes;
@@ -177,6 +195,14 @@ __device__ __forceinline__ u64 insert192(const TableView &t, u64 w0, u64 w1, u64
     atomicAdd(&t.rep->table_overflow, 1ull);
     return kNoIndex;
 }
+
+__device__ __forceinline__ u64 insert192(const TableView &t, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
+    return insert192_hashed(t, rotl64(hash192(w0, w1, w2, len), t.rot), w0, w1, w2, len, add, is_new);
+}
+
+// A ShortSeq192 key on its way through the hash partitions: {w0, w1, w2, meta}, meta = h2 with its low byte replaced
+// by len - 32 (the home slot only needs the top bits of h2).
+__device__ __forceinline__ u64 meta192_of(u64 h2, u32 len) { return (h2 & ~0xFFull) | (u64)(len - 32); }
 
 __device__ __forceinline__ u64 find192(const TableView &t, u64 w0, u64 w1, u64 w2, u32 len) {
     const u64 mask = (1ull << t.log2_cap) - 1;
@@ -231,15 +257,47 @@ static __device__ __noinline__ void insert_unstaged(const TableView &t, u64 key,
     insert64_hashed(t, ((u64)top << 56) | (key & kMask56), key, 1ull, is_new);
     if (is_new) atomicAdd(my_new, 1u);
 }
+// the same for a staged ShortSeq192 record at shared-space address `rec`
+static __device__ __noinline__ void insert_unstaged192(const TableView &t, u32 rec, u32 *my_new) {
+    const ulonglong2 a = lds_v2u64(rec), b = lds_v2u64(rec + 16);
+    bool is_new = false;
+    insert192_hashed(t, b.y & ~0xFFull, a.x, a.y, b.x, (u32)(b.y & 0xFF) + 32, 1ull, is_new);
+    if (is_new) atomicAdd(my_new, 1u);
+}
 
-// Move every complete line (FINAL: everything) of the staging rings to this CTA's segments:
-// partition q's segment starts at seg0 + q * seg_cap (seg_cap a multiple of kLineKeys).  All threads of the
-// CTA call this between two barriers.  s_new is a shared-memory counter of keys created by the overflow path.
-template <bool FINAL>
+// slow paths of the scatter kernels, kept out of line so that they do not cost the hot loop registers
+static __device__ __noinline__ void insert192_slow(const TableView &t, u64 h2, u64 w0, u64 w1, u64 w2, u32 len, u32 *my_new) {
+    bool is_new = false;
+    insert192_hashed(t, h2, w0, w1, w2, len, 1ull, is_new);
+    if (is_new) atomicAdd(my_new, 1u);
+}
+static __device__ __noinline__ void insert64_slow(const TableView &t, u64 h2, u64 key, u32 *my_new) {
+    bool is_new = false;
+    insert64_hashed(t, h2, key, 1ull, is_new);
+    if (is_new) atomicAdd(my_new, 1u);
+}
+
+// Append one ShortSeq192 record to partition `part` (ring of kRingKeys / 4 records).
+__device__ __forceinline__ bool stage_rec192(const Stager &s, u32 part, u64 w0, u64 w1, u64 w2, u64 meta) {
+    constexpr u32 kRingRecs = kRingKeys / 4;
+    const u32 pos = atoms_add_u32(s.head + 4 * part, 1u);
+    if (pos - lds_u32(s.tail + 4 * part) >= kRingRecs) return false;
+    const u32 a = s.ring + 8 * (part * kRingKeys + (pos & (kRingRecs - 1)) * 4);
+    asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(a), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(a + 16), "l"(w2), "l"(meta) : "memory");
+    return true;
+}
+
+// Move every complete line (FINAL: everything) of the staging rings to this CTA's segments.  A record is RW
+// 64-bit words (1: a ShortSeq64 table key, 4: a ShortSeq192 record); head / tail / seg_cap count records, a line is
+// kLineKeys / RW records; partition q's segment starts at seg0 + q * seg_cap * RW.  All threads of the CTA call this
+// between two barriers.  s_new is a shared-memory counter of keys created by the overflow path.
+template <bool FINAL, int RW = 1>
 __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_cap, const TableView &t, int fixed_top,
                                             u32 *s_new) {
     constexpr u32 kLaneGroup = kLineKeys / 2;           // lanes that copy one line (16 bytes each)
     constexpr u32 kGroups = 32 / kLaneGroup;            // lines per warp-wide store
+    constexpr u32 kRingRecs = kRingKeys / RW, kLineRecs = kLineKeys / RW;
     const u32 lane = threadIdx.x & 31;
     const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
     const u32 lt_mask = (1u << lane) - 1;
@@ -247,9 +305,9 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
     for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)kParts; pbase += blockDim.x) {
         const u32 p = pbase + lane;
         const u32 tl = lds_u32(s.tail + 4 * p);
-        const u32 hd = min(lds_u32(s.head + 4 * p), tl + (u32)kRingKeys);
+        const u32 hd = min(lds_u32(s.head + 4 * p), tl + kRingRecs);
         const u32 avail = hd - tl;
-        const u32 nl = avail / kLineKeys;               // 0, 1 or 2 complete lines
+        const u32 nl = avail / kLineRecs;               // 0, 1 or 2 complete lines
         const u32 m1 = __ballot_sync(0xFFFFFFFFu, nl > 0), m2 = __ballot_sync(0xFFFFFFFFu, nl > 1);
         const u32 n1 = __popc(m1), nready = n1 + __popc(m2);
         if (nl > 0) sts_u32(list + 4 * __popc(m1 & lt_mask), lane);
@@ -258,23 +316,32 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
         for (u32 it = g; it < nready; it += kGroups) {   // group g copies the lines it, it + kGroups, ...
             const u32 e = lds_u32(list + 4 * it);
             const u32 q = pbase + (e & 31u);
-            const u32 tq = lds_u32(s.tail + 4 * q) + (e >> 5) * kLineKeys;
-            const ulonglong2 v = lds_v2u64(s.ring + 8 * (q * kRingKeys + (tq & (kRingKeys - 1)) + 2 * sub));
-            if (tq + kLineKeys <= seg_cap) {
-                *reinterpret_cast<ulonglong2 *>(seg0 + (size_t)q * seg_cap + tq + 2 * sub) = v;
-            } else {                                      // segment full
+            const u32 tq = lds_u32(s.tail + 4 * q) + (e >> 5) * kLineRecs;
+            const u32 src = s.ring + 8 * (q * kRingKeys + (tq & (kRingRecs - 1)) * RW + 2 * sub);
+            if (tq + kLineRecs <= seg_cap) {
+                *reinterpret_cast<ulonglong2 *>(seg0 + ((size_t)q * seg_cap + tq) * RW + 2 * sub) = lds_v2u64(src);
+            } else if (RW == 1) {                         // segment full
                 const u32 top = fixed_top >= 0 ? (u32)fixed_top : q;
+                const ulonglong2 v = lds_v2u64(src);
                 insert_unstaged(t, v.x, top, s_new);
                 insert_unstaged(t, v.y, top, s_new);
+            } else if ((sub & 1) == 0) {                  // every second lane takes one whole 32-byte record
+                insert_unstaged192(t, src, s_new);
             }
         }
         __syncwarp();
-        u32 flushed = nl * kLineKeys;
-        if (FINAL) {                                      // the partial last line, key by key (once per CTA)
+        u32 flushed = nl * kLineRecs;
+        if (FINAL) {                                      // the partial last line, record by record (once per CTA)
             for (u32 j = flushed; j < avail; j++) {
-                const u64 key = lds_u64(s.ring + 8 * (p * kRingKeys + ((tl + j) & (kRingKeys - 1))));
-                if (tl + avail <= seg_cap) seg0[(size_t)p * seg_cap + tl + j] = key;
-                else insert_unstaged(t, key, fixed_top >= 0 ? (u32)fixed_top : p, s_new);
+                const u32 rec = s.ring + 8 * (p * kRingKeys + ((tl + j) & (kRingRecs - 1)) * RW);
+                if (tl + avail <= seg_cap) {
+#pragma unroll
+                    for (int w = 0; w < RW; w++) seg0[((size_t)p * seg_cap + tl + j) * RW + w] = lds_u64(rec + 8 * w);
+                } else if (RW == 1) {
+                    insert_unstaged(t, lds_u64(rec), fixed_top >= 0 ? (u32)fixed_top : p, s_new);
+                } else {
+                    insert_unstaged192(t, rec, s_new);
+                }
             }
             flushed = avail;
         }

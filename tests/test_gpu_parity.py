@@ -392,6 +392,37 @@ def test_counter_region_path_table_sizes(sq, oracle, log2_slots):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
 
 
+@pytest.mark.parametrize("skew", [False, True])
+def test_counter_deferred_192(sq, oracle, skew):
+    """ShortSeq192 tables too large for L2: records {w0, w1, w2, meta} are scattered to 256 hash partitions by the pack
+    kernel and inserted partition by partition.  skew: a third of the reads identical (staging ring and segment overrun)."""
+    n, u = 1_500_000, 700_000
+    b = sq.synth_reads(n, u, 33, 96, seed=0x5EED0031)
+    if skew:
+        off = b.offsets.cpu().numpy()
+        L0 = int(off[1] - off[0])
+        a = b.ascii
+        first = a[:L0].clone()
+        lens = np.diff(off)
+        idx = np.nonzero(lens == L0)[0][::2]                 # same-length reads become copies of read 0
+        for i in idx[: n // 3]:
+            a[off[i]: off[i] + L0] = first
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, 1)
+    ctr = sq.DeviceCounter(1, expected_unique=1_000_000)       # 2^21 slots x 32 B = 64 MB > the L2-resident limit
+    assert ctr.capacity() == 1 << 21
+    arr = ctr.pack_count(b)
+    w, l, _ = arr.to_host()
+    assert np.array_equal(w, ow) and np.array_equal(l, ol)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+    ctr.pack_count(b)                                          # second pass over a populated table
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
+
+
 def test_counter_deferred_partition_overflow_and_growth(sq, oracle):
     """Half of the reads are one sequence: its hash partition overflows its buffer and the excess is inserted
     directly; the distinct keys exceed 60 % of the table, so it grows after the pass."""
