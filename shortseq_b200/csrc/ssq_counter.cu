@@ -342,13 +342,22 @@ count_regions_kernel(TableView t, RegionParts rp) {
     u32 my_new = 0, overflow = 0, seg = 0;
     u64 nk[kCountKPT];
     auto load_chunk = [&](u32 c) {
+        const u32 i0 = c * kCountChunk;
+        while (i0 >= pre[seg + 1]) ++seg;                       // warp-uniform: the segment the chunk starts in
+        if (i0 + kCountChunk <= pre[seg + 1]) {                 // the usual case: the whole chunk lies in one segment
+            const u64 *src = rp.keys + (segoff[seg] + (i0 - pre[seg])) + lane;
 #pragma unroll
-        for (int r = 0; r < kCountKPT; r++) {
-            const u32 i = c * kCountChunk + r * 32 + lane;
-            nk[r] = 0;
-            if (i < total) {
-                while (i >= pre[seg + 1]) ++seg;
-                nk[r] = ld_stream_u64(rp.keys + (segoff[seg] + (i - pre[seg])), drop);
+            for (int r = 0; r < kCountKPT; r++) nk[r] = ld_stream_u64(src + r * 32, drop);
+        } else {                                                // it straddles segments or the end of the stream
+            u32 sg = seg;
+#pragma unroll
+            for (int r = 0; r < kCountKPT; r++) {
+                const u32 i = i0 + r * 32 + lane;
+                nk[r] = 0;
+                if (i < total) {
+                    while (i >= pre[sg + 1]) ++sg;
+                    nk[r] = ld_stream_u64(rp.keys + (segoff[sg] + (i - pre[sg])), drop);
+                }
             }
         }
     };
