@@ -36,12 +36,14 @@ __device__ __forceinline__ void deposit64(u32 *stream, int64_t bit, u64 w) {
     if (c) atomicOr(&stream[wi + 2], c);
 }
 
-// Expand stream[] (covering output bytes from index a0, chunk c = 16 bytes) into out[t0, t1).
+// Expand stream[] (covering output bytes from index a0, chunk c = 16 bytes) into out[t0, t1) and leave the words it
+// read (plus the `pad` words deposits may have spilled into) zeroed for the next tile.
 template <int THREADS>
-__device__ __forceinline__ void store_tile(uint8_t *out, int64_t a0, int64_t t0, int64_t t1, const u32 *stream) {
+__device__ __forceinline__ void store_tile(uint8_t *out, int64_t a0, int64_t t0, int64_t t1, u32 *stream, int pad = 0) {
     const int nchunks = (int)((t1 - a0 + 15) >> 4);
     for (int c = threadIdx.x; c < nchunks; c += THREADS) {
         u32 s = stream[c];
+        stream[c] = 0;
         uint4 v = make_uint4(expand4(s & 0xFF), expand4((s >> 8) & 0xFF), expand4((s >> 16) & 0xFF), expand4(s >> 24));
         int64_t idx = a0 + 16 * (int64_t)c;
         if (idx >= t0 && idx + 16 <= t1) {
@@ -55,44 +57,86 @@ __device__ __forceinline__ void store_tile(uint8_t *out, int64_t a0, int64_t t0,
             }
         }
     }
+    if ((int)threadIdx.x < pad) stream[nchunks + threadIdx.x] = 0;
+}
+
+// Persistent CTAs, 2 reads per thread per tile, software-pipelined like the pack kernel: the words, lengths and
+// offsets of the CTA's next tile are loaded while the current tile is deposited and stored.  Two barriers per tile:
+// the store phase clears the stream words it consumed.
+constexpr int kDecRPT = 2;
+constexpr int kDecTile = kThreads * kDecRPT;
+
+template <int W>
+struct DecTile {
+    int64_t t0, t1;
+    int64_t o0[kDecRPT];
+    u64 w[kDecRPT][W];
+    int len[kDecRPT];
+    int nreads;
+};
+
+template <int W>
+__device__ __forceinline__ DecTile<W> load_dec_tile(const u64 *words, const uint8_t *lens, const int64_t *out_off, int64_t n, int64_t tile) {
+    constexpr int MAXLEN = 32 * W;
+    DecTile<W> d;
+    const int64_t first = tile * kDecTile;
+    d.nreads = first < n ? (int)min((int64_t)kDecTile, n - first) : 0;
+    d.t0 = d.t1 = 0;
+    if (d.nreads > 0) { d.t0 = out_off[first]; d.t1 = out_off[first + d.nreads]; }
+#pragma unroll
+    for (int k = 0; k < kDecRPT; k++) {
+        const int r = threadIdx.x + k * kThreads;
+        d.len[k] = -1;
+        d.o0[k] = 0;
+        if (r < d.nreads) {
+            const int64_t i = first + r;
+            d.len[k] = min((int)lens[i], MAXLEN);
+            d.o0[k] = out_off[i];
+#pragma unroll
+            for (int j = 0; j < W; j++) d.w[k][j] = words[(size_t)i * W + j];
+        }
+    }
+    return d;
 }
 
 template <int W>
 __global__ void __launch_bounds__(kThreads) decode_fixed_kernel(const u64 *words, const uint8_t *lens, int64_t n,
                                                                 const int64_t *out_off, uint8_t *out) {
     constexpr int MAXLEN = 32 * W;
-    constexpr int MAX_CHUNKS = (kThreads * MAXLEN + 30) / 16 + 1;
+    constexpr int MAX_CHUNKS = (kDecTile * MAXLEN + 30) / 16 + 1;
     __shared__ u32 stream[MAX_CHUNKS + 3];
     const int64_t mis = (int64_t)((uintptr_t)out & 15);
-    const int64_t ntiles = (n + kThreads - 1) / kThreads;
+    const int64_t ntiles = (n + kDecTile - 1) / kDecTile;
+    for (int c = threadIdx.x; c < MAX_CHUNKS + 3; c += kThreads) stream[c] = 0;
+    DecTile<W> cur = load_dec_tile<W>(words, lens, out_off, n, blockIdx.x);
+    __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t first = tile * kThreads;
-        const int nreads = (int)min((int64_t)kThreads, n - first);
-        const int64_t t0 = out_off[first], t1 = out_off[first + nreads];
-        if (t1 < t0 || t1 - t0 > (int64_t)kThreads * MAXLEN) continue;   // inconsistent offsets: nothing sane to write
+        const int64_t t0 = cur.t0, t1 = cur.t1;
+        const bool sane = t1 >= t0 && t1 - t0 <= (int64_t)kDecTile * MAXLEN;    // inconsistent offsets: nothing sane to write
         const int64_t a0 = ((t0 + mis) & ~(int64_t)15) - mis;
-        const int nchunks = (int)((t1 - a0 + 15) >> 4);
-        for (int c = threadIdx.x; c < nchunks + 3; c += kThreads) stream[c] = 0;
-        __syncthreads();
-        if ((int)threadIdx.x < nreads) {
-            const int64_t i = first + threadIdx.x;
-            const int len = min((int)lens[i], MAXLEN);
-            const int64_t o0 = out_off[i];
-            if (o0 >= t0 && o0 + len <= t1) {
+        if (sane) {
 #pragma unroll
-                for (int k = 0; k < W; k++) {
-                    int nb = 2 * len - 64 * k;
-                    if (nb > 0) {
-                        u64 w = words[(size_t)i * W + k];
-                        if (nb < 64) w &= (1ull << nb) - 1;
-                        deposit64(stream, 2 * (o0 - a0) + 64 * k, w);
+            for (int k = 0; k < kDecRPT; k++) {
+                const int len = cur.len[k];
+                const int64_t o0 = cur.o0[k];
+                if (len >= 0 && o0 >= t0 && o0 + len <= t1) {
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        const int nb = 2 * len - 64 * j;
+                        if (nb > 0) {
+                            u64 w = cur.w[k][j];
+                            if (nb < 64) w &= (1ull << nb) - 1;
+                            deposit64(stream, 2 * (o0 - a0) + 64 * j, w);
+                        }
                     }
                 }
             }
         }
+        const DecTile<W> nxt = load_dec_tile<W>(words, lens, out_off, n, tile + gridDim.x);   // in flight during the store phase
         __syncthreads();
-        store_tile<kThreads>(out, a0, t0, t1, stream);
+        if (sane) store_tile<kThreads>(out, a0, t0, t1, stream, 3);
         __syncthreads();
+        cur = nxt;
     }
 }
 
@@ -289,7 +333,7 @@ int ssq_decode64(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64
     if (n == 0) return SSQ_OK;
     SSQ_ARG(words && lens && out_offsets && ascii_out, "NULL buffer");
     DeviceGuard g(ctx->device);
-    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    int grid = grid_for(ctx, (n + kDecTile - 1) / kDecTile, 8);
     decode_fixed_kernel<1><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
@@ -301,7 +345,7 @@ int ssq_decode192(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int6
     if (n == 0) return SSQ_OK;
     SSQ_ARG(words && lens && out_offsets && ascii_out, "NULL buffer");
     DeviceGuard g(ctx->device);
-    int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+    int grid = grid_for(ctx, (n + kDecTile - 1) / kDecTile, 8);
     decode_fixed_kernel<3><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;

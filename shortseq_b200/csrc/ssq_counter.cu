@@ -207,11 +207,12 @@ constexpr int kMaxStreamSegs = 512;
 // Level 2: CTA (p, s) reads slice s of the level-1 segments of partition p (scatter CTAs [c0, c1)) and appends
 // every key to the segment of its level-2 partition (hash bits 55..48).  The loads of the next tile are in
 // flight while the current tile is staged and flushed.
-__global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp) {
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[kParts], s_tail[kParts];
     __shared__ u32 pre[kMaxStreamSegs + 1];
-    __shared__ u32 s_list[(kThreads / 32) * 64];
+    __shared__ u32 s_list[(kParts / 32) * 64];
     __shared__ u32 s_unstaged_new;
     const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     const u32 p = blockIdx.x / rp.slices, s = blockIdx.x - p * rp.slices;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     const u64 drop = l2_policy_evict_first();
     const u64 *const part0 = pv.keys + ((size_t)c0 * kParts + p) * pv.seg_cap;     // segment k starts at part0 + k * seg_stride
     const size_t seg_stride = (size_t)kParts * pv.seg_cap;
-    constexpr u32 kTile = kThreads * kScatterRounds;
+    constexpr u32 kTile = THREADS * kScatterRounds;
     // Tiles never straddle segments, so a tile's keys sit at consecutive addresses.  (seg, pos) = where the next tile
     // to LOAD starts; both are CTA-uniform.
     u32 seg = 0, pos = 0;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
         const u32 here = min(pre[seg + 1] - pre[seg] - pos, kTile);
         const u64 *src = part0 + seg * seg_stride + pos + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < kScatterRounds; j++) nk[j] = (u32)(j * kThreads) + threadIdx.x < here ? ld_stream_u64(src + j * kThreads, drop) : 0ull;
+        for (int j = 0; j < kScatterRounds; j++) nk[j] = (u32)(j * THREADS) + threadIdx.x < here ? ld_stream_u64(src + j * THREADS, drop) : 0ull;
         pos += here;
         return here;
     };
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 3) region_scatter_kernel(TableView t
     }
     flush_lines<true>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
     __syncthreads();
-    rp.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = stager_seg_count(stg, threadIdx.x, rp.seg_cap);
+    if (threadIdx.x < (u32)kParts) rp.seg_count[(size_t)blockIdx.x * kParts + threadIdx.x] = stager_seg_count(stg, threadIdx.x, rp.seg_cap);
     if (threadIdx.x == 0 && s_unstaged_new) atomicAdd(t.size, (u64)s_unstaged_new);
 }
 
@@ -1009,9 +1010,15 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     RegionParts rp;
     int rc = prepare_regions(c, n, &rp);
     if (rc) return rc;
-    rc = set_max_smem((const void *)region_scatter_kernel, kStagerRingBytes);
-    if (rc) return rc;
-    region_scatter_kernel<<<kParts * rp.slices, kThreads, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+    if (env_int("SSQ_SCATTER_THREADS", 384, 256, 384) == 384) {
+        rc = set_max_smem((const void *)region_scatter_kernel<384>, kStagerRingBytes);
+        if (rc) return rc;
+        region_scatter_kernel<384><<<kParts * rp.slices, 384, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+    } else {
+        rc = set_max_smem((const void *)region_scatter_kernel<256>, kStagerRingBytes);
+        if (rc) return rc;
+        region_scatter_kernel<256><<<kParts * rp.slices, 256, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+    }
     SSQ_LAUNCH_CHECK();
     if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
     const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
