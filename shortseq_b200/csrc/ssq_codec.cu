@@ -357,7 +357,7 @@ int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, 
     if (n == 0) return SSQ_OK;
     SSQ_ARG(words && word_off && lens && out_offsets && ascii_out, "NULL buffer");
     DeviceGuard g(ctx->device);
-    int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, 4);
+    int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, 8);
     decode_var_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;

@@ -523,7 +523,7 @@ int ssq_packvar(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const i
     if (rc || n == 0) return rc;
     PackArgs a{ascii, 0, ascii_bytes, offsets, n, 0, (u64 *)words, lens, word_off, ctx->d_report};
     int64_t ntiles = (n + kVarTileReads - 1) / kVarTileReads;
-    int grid = grid_for(ctx, ntiles, 4);
+    int grid = grid_for(ctx, ntiles, 8);
     pack_var_kernel<<<grid, kPackThreads, 0, ctx->stream>>>(a);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
