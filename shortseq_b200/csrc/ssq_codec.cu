@@ -259,9 +259,22 @@ __global__ void __launch_bounds__(kThreads) refset_kernel(const u64 *q, const ui
             const int cnt = min(kRefChunk, nr - r0);
             __syncthreads();
             for (int k = threadIdx.x; k < cnt * W; k += kThreads) s_ref[k] = refs[(size_t)r0 * W + k];
-            for (int k = threadIdx.x; k < cnt; k += kThreads) s_len[k] = lr[r0 + k];
-            __syncthreads();
-            if (mine) {
+            int same = 1;
+            const int len0 = lr[r0];
+            for (int k = threadIdx.x; k < cnt; k += kThreads) { const uint8_t l = lr[r0 + k]; s_len[k] = l; same &= l == len0; }
+            const int uniform = __syncthreads_and(same);      // the usual case: every reference of the chunk has one length
+            if (mine && uniform) {
+                if (qlen == len0) {
+#pragma unroll 4
+                    for (int j = 0; j < cnt; j++) {
+                        int d = 0;
+#pragma unroll
+                        for (int k = 0; k < W; k++) d += diff_bases(qw[k], s_ref[j * W + k]);
+                        if (d < best) { best = d; best_j = (u32)(r0 + j); }
+                        within += d <= thresh ? 1 : 0;
+                    }
+                }
+            } else if (mine) {
                 for (int j = 0; j < cnt; j++) {
                     if (s_len[j] != qlen) continue;
                     int d = 0;

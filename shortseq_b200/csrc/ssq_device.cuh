@@ -183,11 +183,14 @@ __host__ __device__ __forceinline__ bool is_acgt(uint8_t c) {
 }
 
 // popcount(((x>>1)|x) & 0x5555...) -- number of differing bases of one block
-// (short_seq_64.pyx:82-84 of the reference).
+// (short_seq_64.pyx:82-84 of the reference).  The indicator bits sit at even positions only, so the high half is
+// slid into the odd positions of the low half and ONE 32-bit POPC counts all 32 bases (POPC is a quarter-rate pipe).
 __device__ __forceinline__ int diff_bases(u64 a, u64 b) {
-    u64 x = a ^ b;
-    x = ((x >> 1) | x) & 0x5555555555555555ull;
-    return __popcll(x);
+    const u64 x = a ^ b;
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    const u32 ylo = ((lo >> 1) | lo) & 0x55555555u;
+    const u32 yhi = ((hi >> 1) | hi) & 0x55555555u;
+    return __popc(ylo | (yhi << 1));
 }
 
 }  // namespace ssq
