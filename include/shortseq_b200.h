@@ -218,6 +218,20 @@ int ssq_host_pack_count(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii,
 int ssq_host_pack_count_lens(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii, const uint8_t *h_lens,
                              int64_t n, uint64_t *h_words, int64_t chunk_reads, ssq_report *report);
 
+/* ---- FASTQ ingest ----------------------------------------------------------
+ * Replaces read_and_count_fastq (counter.pyx:57-71) and its getline loop (fast_read.pyx:3-20): h_text is the whole
+ * FASTQ file in host memory; every line whose 1-based number is 2 mod 4 is a read, minus its last byte (the newline --
+ * or the last base of an unterminated final line, which the reference drops too, short_seq.pyx:50-52).  The text goes
+ * to the GPU in chunks of chunk_bytes (0 = 256 MB); newline scan, line selection, gather into ASCII + offsets and the
+ * fused pack+count all run on the device.  Reads of 0..32 nt are counted into c64, 33..96 nt into c192 (either may be
+ * NULL when the file holds no such read).  n_reads = reads seen; n_longer / first_longer = number and lowest read
+ * number of reads longer than 96 nt (not counted: SSQ_CLASS_VAR keys cannot be deduplicated by the reference either).
+ * report = lowest read number with a bad base (code SSQ_ERR_BAD_BASE); counting stops at the chunk that holds it.
+ * track_first_index != 0 records first-occurrence read numbers for ssq_counter_export (dict order). */
+int ssq_host_fastq_count(ssq_ctx *ctx, ssq_counter *c64, ssq_counter *c192, const uint8_t *h_text, int64_t nbytes,
+                         int64_t chunk_bytes, int track_first_index, int64_t *n_reads, int64_t *n_longer,
+                         int64_t *first_longer, ssq_report *report);
+
 /* ---- synthetic reads (measurement tooling) ----------------
  * Deterministic counter-based generator, identical to oracle/ssq_oracle.c's
  * ssq_oracle_synth_reads.  offsets[n+1] and ascii are outputs; ascii must hold

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from . import batch as _batch
 from ._lib import CLASS_64, CLASS_192, CLASS_VAR
-from ._runtime import MSG_TOO_LONG, context, gather_reads, ptr, words_to_numpy
+from ._runtime import MSG_TOO_LONG, bad_base_message, context, gather_reads, ptr, words_to_numpy
 from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box
 
 
@@ -233,15 +233,64 @@ class ShortSeqCounter(dict):
         return self
 
 
-def read_and_count_fastq(filename):
-    """Count the sequence lines of a FASTQ file (reference counter.pyx:57-71, fast_read.pyx:3-20).
+def _fastq_reads_host(data, upto=None):
+    """Host restatement of the reference's line selection (for error messages and the oracle tests): the reads of a
+    FASTQ buffer, each minus its last byte."""
+    buf = bytes(data)
+    reads, pos, count = [], 0, 1
+    while pos < len(buf):
+        nl = buf.find(b"\n", pos)                      # getline: lines end at '\n' only
+        end = len(buf) if nl < 0 else nl + 1
+        if count % 2 == 0 and count % 4 != 0:
+            reads.append(buf[pos:end - 1])
+            if upto is not None and len(reads) > upto:
+                break
+        pos, count = end, count + 1
+    return reads
 
-    Every 4k+2-th line is a read; like the reference's `_from_chars`, the last byte of the line
-    (the newline) is dropped unconditionally (SURVEY trap T9).
+
+def read_and_count_fastq(filename, device=None, chunk_bytes=0):
+    """Count the sequence lines of a FASTQ file (reference counter.pyx:57-71, fast_read.pyx:3-20) on the GPU.
+
+    Every 4k+2-th line is a read; like the reference's `_from_chars`, the last byte of the line (the newline) is
+    dropped unconditionally (SURVEY trap T9).  The file is shipped to the device as raw text: newline scan, line
+    selection, gather, pack and count all run there (ssq_host_fastq_count); only the distinct sequences come back.
     """
-    reads = []
-    with open(filename, "rb") as f:
-        for count, line in enumerate(f, start=1):
-            if count % 2 == 0 and count % 4 != 0:
-                reads.append(line[:-1])
-    return ShortSeqCounter(reads)
+    data = np.fromfile(filename, dtype=np.uint8)
+    ctx = context(device)
+    self = ShortSeqCounter()
+    if data.size == 0:
+        return self
+    c64 = DeviceCounter(CLASS_64, expected_unique=0, device=ctx.device)
+    c192 = DeviceCounter(CLASS_192, expected_unique=0, device=ctx.device)
+    n_reads, n_longer, first_longer = C.c_int64(), C.c_int64(), C.c_int64()
+    rep = _lib.Report()
+    h = ctx.bind()
+    _lib.check(_lib.lib().ssq_host_fastq_count(h, c64.handle, c192.handle, data.ctypes.data, int(data.size), int(chunk_bytes), 1,
+                                               C.byref(n_reads), C.byref(n_longer), C.byref(first_longer), C.byref(rep)))
+    bad = rep.first_bad_read if rep.code != _lib.OK else -1
+    if n_longer.value and (bad < 0 or first_longer.value < bad):
+        read = _fastq_reads_host(data, upto=first_longer.value)[first_longer.value]
+        if len(read) > 1024:
+            raise Exception(MSG_TOO_LONG)
+        raise NotImplementedError("read_and_count_fastq: reads longer than 96 nt (ShortSeqVar) are not counted -- the reference "
+                                  "does not deduplicate them either (each occurrence becomes its own key)")
+    if rep.code == _lib.ERR_TABLE_FULL:
+        raise _lib.LibraryError("counter table overflow")
+    if bad >= 0:
+        read = _fastq_reads_host(data, upto=bad)[bad]
+        raise Exception(bad_base_message(read))
+    items = []
+    for klass, ctr in ((CLASS_64, c64), (CLASS_192, c192)):
+        if len(ctr) == 0:
+            continue
+        keys, counts, first, _ = ctr.export(1, with_first_index=True)
+        w, l, _ = keys.to_host()
+        cnt, fi = counts.cpu().numpy(), first.cpu().numpy()
+        for j in range(len(l)):
+            words = (int(w[j]),) if klass == CLASS_64 else tuple(int(x) for x in w[j])
+            items.append((int(fi[j]), klass, words, int(l[j]), int(cnt[j])))
+    items.sort()
+    for _, klass, words, length, count in items:
+        dict.__setitem__(self, _box(klass, words, length), count)
+    return self

@@ -94,16 +94,17 @@ __global__ void __launch_bounds__(kThreads) lookup_kernel(TableView t, const u64
     }
 }
 
+// indices == nullptr: key i occurred at read base_index + i; else at read base_index + indices[i]
 template <int KLASS>
 __global__ void __launch_bounds__(kThreads) first_index_kernel(TableView t, const u64 *words, const uint8_t *lens,
-                                                               int64_t n, int64_t base_index) {
+                                                               int64_t n, int64_t base_index, const int64_t *indices) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         u32 len = lens[i];
         if (!len_in_class(KLASS, len)) continue;
         u64 s;
         if constexpr (KLASS == SSQ_CLASS_64) s = find64(t, words[i], len);
         else s = find192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], len);
-        if (s != kNoIndex) red_min_u64(t.first_idx + s, (u64)(base_index + i));
+        if (s != kNoIndex) red_min_u64(t.first_idx + s, (u64)(base_index + (indices ? indices[i] : i)));
     }
 }
 
@@ -1245,6 +1246,14 @@ int ssq_counter_pack_count(ssq_counter *c, const uint8_t *ascii, int64_t ascii_b
 int ssq_counter_first_index(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n, int64_t base_index) {
     SSQ_ARG(c != nullptr, "counter is NULL");
     SSQ_ARG(n >= 0 && (n == 0 || (words != nullptr && lens != nullptr)), "bad batch");
+    return counter_first_index_indexed(c, (const u64 *)words, lens, n, nullptr, base_index);
+}
+
+}  // extern "C"
+
+namespace ssq {
+int counter_first_index_indexed(ssq_counter *c, const u64 *words, const uint8_t *lens, int64_t n, const int64_t *indices,
+                                int64_t base_index) {
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
     if (!c->first_idx) {
@@ -1256,12 +1265,15 @@ int ssq_counter_first_index(ssq_counter *c, const uint64_t *words, const uint8_t
     int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
     TableView t = view_of(c);
     if (c->klass == SSQ_CLASS_64)
-        first_index_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index);
+        first_index_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index, indices);
     else
-        first_index_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index);
+        first_index_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, (const u64 *)words, lens, n, base_index, indices);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
+}  // namespace ssq
+
+extern "C" {
 
 int ssq_counter_lookup(ssq_counter *c, const uint64_t *words, const uint8_t *lens, int64_t n, uint64_t *counts) {
     SSQ_ARG(c != nullptr, "counter is NULL");

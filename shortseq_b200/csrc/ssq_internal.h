@@ -108,6 +108,11 @@ int ctx_scratch(ssq_ctx *ctx, size_t bytes, void **out);
 int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi, const int64_t *offsets, int64_t n,
                     int64_t index_base, u64 *words, uint8_t *lens);
 
+// first-occurrence tracking with explicit read numbers (ssq_counter.cu): key i occurred at base_index + indices[i]
+// (indices == nullptr: base_index + i)
+int counter_first_index_indexed(ssq_counter *c, const u64 *words, const uint8_t *lens, int64_t n, const int64_t *indices,
+                                int64_t base_index);
+
 // exclusive scan helpers (ssq_scan.cu)
 int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out);
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off);

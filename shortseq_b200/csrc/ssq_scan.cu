@@ -26,6 +26,18 @@ struct VarWords {
         return (len < 0 || len > 1024) ? 0 : (len + 31) >> 5;
     }
 };
+// FASTQ ingest (ssq_fastq.cu): 1 for the reads of a length class; length of the j-th selected read
+struct FastqClassFlag {
+    const int64_t *starts, *ends; int klass;
+    __device__ int64_t operator()(int64_t k) const {
+        const int64_t len = ends[k] - starts[k];
+        return (klass == SSQ_CLASS_64 ? (len >= 0 && len <= 32) : (len >= 33 && len <= 96)) ? 1 : 0;
+    }
+};
+struct FastqSelLen {
+    const int64_t *starts, *ends, *sel;
+    __device__ int64_t operator()(int64_t j) const { const int64_t k = sel ? sel[j] : j; return ends[k] - starts[k]; }
+};
 struct SynthLen {
     uint64_t seed; int64_t first, n_keys; int32_t lo, hi;
     __device__ int64_t operator()(int64_t i) const {
@@ -143,6 +155,14 @@ int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t 
 
 int scan_u32_counts(ssq_ctx *ctx, const u32 *counts, int64_t n, int64_t *out) {
     return scan_exclusive(ctx, CountU32{counts}, n, out);
+}
+
+int scan_fastq_flags(ssq_ctx *ctx, const int64_t *starts, const int64_t *ends, int klass, int64_t n, int64_t *out) {
+    return scan_exclusive(ctx, FastqClassFlag{starts, ends, klass}, n, out);
+}
+
+int scan_fastq_lens(ssq_ctx *ctx, const int64_t *starts, const int64_t *ends, const int64_t *sel, int64_t n, int64_t *out) {
+    return scan_exclusive(ctx, FastqSelLen{starts, ends, sel}, n, out);
 }
 
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off) {
