@@ -13,7 +13,7 @@ from . import _lib
 from . import batch as _batch
 from ._lib import CLASS_64, CLASS_192, CLASS_VAR
 from ._runtime import MSG_TOO_LONG, bad_base_message, context, gather_reads, ptr, words_to_numpy
-from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box
+from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box, _box_many
 
 
 class DeviceCounter:
@@ -146,7 +146,7 @@ class DeviceCounter:
 def count_reads(reads, device=None):
     """Count a list of bytes of mixed lengths on the GPU.
 
-    -> list of (klass, words tuple, length, count, first_index) in first-occurrence order.
+    -> one (klass, words, lens, counts, first_index) tuple of host arrays per length class present.
     ShortSeqVar-length reads cannot be deduplicated by the reference (its dict hashes the heap
     pointer, SURVEY trap T3); they are rejected here rather than silently diverging.
     """
@@ -161,7 +161,7 @@ def count_reads(reads, device=None):
         errors.append((int(var[0]), NotImplementedError(
             "ShortSeqCounter: reads longer than 96 nt (ShortSeqVar) are not counted -- the reference does not "
             "deduplicate them either (each occurrence becomes its own key)")))
-    out = []
+    groups = []
     for k, idx, sub_ascii, sub_off in _batch.split_by_class(h_ascii, h_off):
         if k == CLASS_VAR:
             continue
@@ -178,15 +178,24 @@ def count_reads(reads, device=None):
         ctr.track_first_index(arr)
         keys, counts, first, _ = ctr.export(1, with_first_index=True)
         w, l, _ = keys.to_host()
-        cnt = counts.cpu().numpy()
-        fi = idx[first.cpu().numpy()]          # position in the original list
-        for j in range(len(l)):
-            words = (int(w[j]),) if k == CLASS_64 else tuple(int(x) for x in w[j])
-            out.append((k, words, int(l[j]), int(cnt[j]), int(fi[j])))
+        groups.append((k, w, l, counts.cpu().numpy(), idx[first.cpu().numpy()]))   # first = position in the original list
     if errors:
         raise min(errors, key=lambda t: t[0])[1]
-    out.sort(key=lambda t: t[4])
-    return out
+    return groups
+
+
+def _fill_in_order(dst, groups):
+    """Insert the per-class results (klass, words, lens, counts, first_index arrays) into the dict `dst` in
+    first-occurrence order.  Boxing and the insertion loop run in bulk (dict.update over a zip)."""
+    objs, counts, firsts = [], [], []
+    for klass, w, l, cnt, fi in groups:
+        objs += _box_many(klass, w, l)
+        counts += np.asarray(cnt).tolist()
+        firsts.append(np.asarray(fi, dtype=np.int64))
+    if not objs:
+        return
+    order = np.argsort(np.concatenate(firsts), kind="stable").tolist()
+    dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
 
 
 class ShortSeqCounter(dict):
@@ -210,9 +219,12 @@ class ShortSeqCounter(dict):
     def _count_py_bytes_list(self, it):
         if not it:
             return
-        for klass, words, length, count, _ in count_reads(it):
-            key = _box(klass, words, length)
-            dict.__setitem__(self, key, dict.get(self, key, 0) + count)
+        if len(self) == 0:
+            _fill_in_order(self, count_reads(it))
+            return
+        for klass, w, l, cnt, _ in count_reads(it):                 # adding to a non-empty counter
+            for key, count in zip(_box_many(klass, w, l), np.asarray(cnt).tolist()):
+                dict.__setitem__(self, key, dict.get(self, key, 0) + count)
 
     @classmethod
     def from_batch(cls, source, offsets=None, klass=None, device=None):
@@ -227,9 +239,7 @@ class ShortSeqCounter(dict):
         w, l, _ = keys.to_host()
         cnt, fi = counts.cpu().numpy(), first.cpu().numpy()
         self = cls()
-        for j in np.argsort(fi, kind="stable"):
-            words = (int(w[j]),) if klass == CLASS_64 else tuple(int(x) for x in w[j])
-            dict.__setitem__(self, _box(klass, words, int(l[j])), int(cnt[j]))
+        _fill_in_order(self, [(klass, w, l, cnt, fi)])
         return self
 
 
@@ -280,17 +290,12 @@ def read_and_count_fastq(filename, device=None, chunk_bytes=0):
     if bad >= 0:
         read = _fastq_reads_host(data, upto=bad)[bad]
         raise Exception(bad_base_message(read))
-    items = []
+    groups = []
     for klass, ctr in ((CLASS_64, c64), (CLASS_192, c192)):
         if len(ctr) == 0:
             continue
         keys, counts, first, _ = ctr.export(1, with_first_index=True)
         w, l, _ = keys.to_host()
-        cnt, fi = counts.cpu().numpy(), first.cpu().numpy()
-        for j in range(len(l)):
-            words = (int(w[j]),) if klass == CLASS_64 else tuple(int(x) for x in w[j])
-            items.append((int(fi[j]), klass, words, int(l[j]), int(cnt[j])))
-    items.sort()
-    for _, klass, words, length, count in items:
-        dict.__setitem__(self, _box(klass, words, length), count)
+        groups.append((klass, w, l, counts.cpu().numpy(), first.cpu().numpy()))
+    _fill_in_order(self, groups)
     return self

@@ -37,9 +37,10 @@ def _nblocks(length):
 
 
 class _ShortSeqBase:
-    """Shared protocol.  `_packed` is a tuple of Python ints (uint64 blocks), `_length` an int."""
+    """Shared protocol.  `_packed` is a tuple of Python ints (uint64 blocks), `_length` an int, `_hash` the
+    precomputed `hash()` (the reference also hashes in O(1): it returns the first block)."""
 
-    __slots__ = ("_packed", "_length")
+    __slots__ = ("_packed", "_length", "_hash")
     _klass = None
 
     def __init__(self, *a, **k):
@@ -47,10 +48,7 @@ class _ShortSeqBase:
 
     def __hash__(self):
         # prehash = first block, seen as Py_hash_t (reference short_seq_64.pyx:35-36; -1 -> -2 by CPython)
-        h = self._packed[0]
-        if h >= 1 << 63:
-            h -= 1 << 64
-        return -2 if h == -1 else h
+        return self._hash
 
     def __len__(self):
         return self._length
@@ -139,13 +137,42 @@ class ShortSeqVar(_ShortSeqBase):
 _TYPES = {CLASS_64: ShortSeq64, CLASS_192: ShortSeq192, CLASS_VAR: ShortSeqVar}
 
 
+def _hash_of_block(h):
+    if h >= 1 << 63:
+        h -= 1 << 64
+    return -2 if h == -1 else h
+
+
 def _box(klass, packed, length):
     """Build a ShortSeq object from its class, blocks and length (no validation)."""
     cls = _TYPES[klass]
     obj = object.__new__(cls)
-    object.__setattr__(obj, "_packed", tuple(int(x) & _M64 for x in packed))
-    object.__setattr__(obj, "_length", int(length))
+    obj._packed = tuple(int(x) & _M64 for x in packed)
+    obj._length = int(length)
+    obj._hash = _hash_of_block(obj._packed[0])
     return obj
+
+
+def _box_many(klass, words, lens):
+    """Box a whole array of fixed-class keys: words uint64 ndarray [n] (ShortSeq64) or [n, 3] (ShortSeq192), lens
+    ndarray [n] -> list of ShortSeq objects.  The per-object work is three slot stores; blocks, lengths and hashes are
+    converted to Python ints in bulk."""
+    cls = _TYPES[klass]
+    w = np.ascontiguousarray(words).view(np.uint64)
+    first = w if w.ndim == 1 else w[:, 0]
+    hashes = first.view(np.int64).copy()
+    hashes[hashes == -1] = -2
+    packed = [(x,) for x in w.tolist()] if w.ndim == 1 else [tuple(r) for r in w.tolist()]
+    new = object.__new__
+    out = []
+    append = out.append
+    for p, l, h in zip(packed, np.asarray(lens).tolist(), hashes.tolist()):
+        o = new(cls)
+        o._packed = p
+        o._length = l
+        o._hash = h
+        append(o)
+    return out
 
 
 empty = _box(CLASS_64, (0,), 0)   # module singleton, like the reference's (short_seq.pyx:7)
