@@ -333,8 +333,10 @@ count_regions_kernel(TableView t, RegionParts rp) {
     }
     const u64 keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
+    // a region nobody has inserted into yet (first pass over a cleared table) is known to be all zero: nothing to read
+    const bool was_empty = t.region_count[region] == 0;
     for (u32 i = threadIdx.x; i < R; i += THREADS) {
-        ks[i] = ld_hint_v2u64(gslots + i, keep).x;
+        ks[i] = was_empty ? 0ull : ld_hint_v2u64(gslots + i, keep).x;
         ds[i] = 0;
     }
     __syncthreads();
@@ -417,10 +419,7 @@ count_regions_kernel(TableView t, RegionParts rp) {
     __syncthreads();
     for (u32 i = threadIdx.x; i < R; i += THREADS) {
         const u32 d = ds[i];
-        if (d) {
-            const ulonglong2 old = gslots[i];
-            gslots[i] = make_ulonglong2(ks[i], old.y + d);
-        }
+        if (d) gslots[i] = make_ulonglong2(ks[i], (was_empty ? 0ull : gslots[i].y) + d);
     }
     if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
     // keys created in this region: table size and the region's occupancy
