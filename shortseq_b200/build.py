@@ -50,7 +50,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     for src, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed for {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"])
     return lib
 
 

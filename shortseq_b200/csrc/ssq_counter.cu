@@ -209,7 +209,7 @@ constexpr int kMaxStreamSegs = 512;
 // every key to the segment of its level-2 partition (hash bits 55..48).  The loads of the next tile are in
 // flight while the current tile is staged and flushed.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp) {
+__global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t, PartView pv, RegionParts rp, u32 flush_keys) {
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[kParts], s_tail[kParts];
     __shared__ u32 pre[kMaxStreamSegs + 1];
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t,
             if (k[j] == 0) continue;
             if (!stage_key(stg, (u32)(k[j] >> 48) & 0xFFu, k[j])) insert_unstaged(t, k[j], p, &s_unstaged_new);
         }
-        if (unflushed >= kTile / 2 || !have) {   // a short tail tile waits for the next one
+        if (unflushed >= flush_keys || !have) {   // flush once enough keys are staged (a short tail tile waits for the next one)
             unflushed = 0;
             __syncthreads();
             flush_lines<false>(stg, seg0, rp.seg_cap, t, (int)p, &s_unstaged_new);
@@ -1013,11 +1013,11 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     if (env_int("SSQ_SCATTER_THREADS", 384, 256, 384) == 384) {
         rc = set_max_smem((const void *)region_scatter_kernel<384>, kStagerRingBytes);
         if (rc) return rc;
-        region_scatter_kernel<384><<<kParts * rp.slices, 384, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+        region_scatter_kernel<384><<<kParts * rp.slices, 384, kStagerRingBytes, ctx->stream>>>(t, pv, rp, (u32)env_int("SSQ_SCATTER_FLUSH_KEYS", 768, 1, 4096));
     } else {
         rc = set_max_smem((const void *)region_scatter_kernel<256>, kStagerRingBytes);
         if (rc) return rc;
-        region_scatter_kernel<256><<<kParts * rp.slices, 256, kStagerRingBytes, ctx->stream>>>(t, pv, rp);
+        region_scatter_kernel<256><<<kParts * rp.slices, 256, kStagerRingBytes, ctx->stream>>>(t, pv, rp, (u32)env_int("SSQ_SCATTER_FLUSH_KEYS", 512, 1, 4096));
     }
     SSQ_LAUNCH_CHECK();
     if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
