@@ -904,8 +904,9 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     const int line = kLineKeys / rw;                        // records per 128-byte line
     // a CTA sees ~n/grid keys, 1/256 of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
     int64_t per = n / ((int64_t)grid * kParts);
-    per = per + per / 16 + 64;
+    per = per + per * env_int("SSQ_SEG_SLACK_PCT", 6, 0, 100) / 100 + env_int("SSQ_SEG_SLACK_ABS", 64, 0, 1 << 20);   // tests shrink the slack
     per = (per + line - 1) & ~(int64_t)(line - 1);
+    if (per < line) per = line;
     // ShortSeq192 overflow segments: 2 % of a CTA's reads + slack
     const int64_t ovf_cap = c->klass == SSQ_CLASS_64 ? 0 : n / grid / 50 + 256;
     const int64_t main_entries = per * grid * kParts * rw;
@@ -960,8 +961,9 @@ static int prepare_regions(ssq_counter *c, int64_t n, RegionParts *rp) {
     const int slices = region_slices();
     if ((slices << (8 - qbits)) > kMaxRegionSegs) { set_error("too many level-2 segments per region"); return SSQ_ERR_ARG; }
     int64_t per = n / ((int64_t)kParts * slices * kParts);
-    per = per + per / 16 + 64;
+    per = per + per * env_int("SSQ_SEG_SLACK_PCT", 6, 0, 100) / 100 + env_int("SSQ_SEG_SLACK_ABS", 64, 0, 1 << 20);
     per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
+    if (per < kLineKeys) per = kLineKeys;
     const int64_t nseg = (int64_t)kParts * slices * kParts;
     const int64_t need = per * nseg;
     if (need > c->region_cap) {

@@ -330,11 +330,12 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
             }
         }
         __syncwarp();
-        u32 flushed = nl * kLineRecs;
+        u32 new_tail = tl + nl * kLineRecs;
         if (FINAL) {                                      // the partial last line, record by record (once per CTA)
-            for (u32 j = flushed; j < avail; j++) {
+            const bool fits = tl + avail <= seg_cap;
+            for (u32 j = nl * kLineRecs; j < avail; j++) {
                 const u32 rec = s.ring + 8 * (p * kRingKeys + ((tl + j) & (kRingRecs - 1)) * RW);
-                if (tl + avail <= seg_cap) {
+                if (fits) {
 #pragma unroll
                     for (int w = 0; w < RW; w++) seg0[((size_t)p * seg_cap + tl + j) * RW + w] = lds_u64(rec + 8 * w);
                 } else if (RW == 1) {
@@ -343,9 +344,11 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
                     insert_unstaged192(t, rec, s_new);
                 }
             }
-            flushed = avail;
+            // after the final flush the tail is what stager_seg_count reports: the entries that really are in the
+            // segment (whole lines up to seg_cap, plus the partial line only if it fitted)
+            new_tail = fits ? tl + avail : min(new_tail, seg_cap);
         }
-        sts_u32(s.tail + 4 * p, tl + flushed);
+        sts_u32(s.tail + 4 * p, new_tail);
         sts_u32(s.head + 4 * p, hd);
     }
 }

@@ -423,6 +423,29 @@ def test_counter_deferred_192(sq, oracle, skew):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
 
 
+@pytest.mark.parametrize("klass", [0, 1])
+def test_counter_deferred_tight_segments(sq, oracle, klass, monkeypatch):
+    """Partition segments sized with no slack at all: about half of them overflow by a few keys, so every way a segment
+    can end (full lines up to the cap, a partial last line that fits or does not) occurs; the excess is inserted
+    directly and the counts stay exact."""
+    monkeypatch.setenv("SSQ_SEG_SLACK_PCT", "0")
+    monkeypatch.setenv("SSQ_SEG_SLACK_ABS", "0")
+    n, u = (3_000_000, 1_400_000) if klass == 0 else (1_500_000, 700_000)
+    lo, hi = (20, 32) if klass == 0 else (33, 96)
+    b = sq.synth_reads(n, u, lo, hi, seed=0x5EED0051)
+    (ow, ol), expect = _oracle_counts_of_batch(oracle, b, klass)
+    ctr = sq.DeviceCounter(klass, expected_unique=2_000_000 if klass == 0 else 1_000_000)
+    # a first pass over other reads leaves stale keys in the partition buffers: entries past a segment's real end
+    # must never be read back
+    ctr.pack_count(sq.synth_reads(n, u, lo, hi, seed=0x5EED0052))
+    ctr.clear()
+    ctr.pack_count(b)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+
+
 def test_counter_deferred_partition_overflow_and_growth(sq, oracle):
     """Half of the reads are one sequence: its hash partition overflows its buffer and the excess is inserted
     directly; the distinct keys exceed 60 % of the table, so it grows after the pass."""
