@@ -382,6 +382,7 @@ def run_ours(args):
     dom = max(kernels, key=lambda kk: kk["ms_per_launch"])
     # top level = the dominant kernel (most device time per step); "pass" = all kernels of one ssq_counter_pack_count
     roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "frac_of_8tbs_spec": round(dom["achieved_gbs"] / 8000.0, 4),
                 "traffic": dom["traffic"], "kernel": dom["kernel"], "kernel_ms_per_launch": dom["ms_per_launch"],
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "peak_source": peak_src,
                 "pass": {"kernels": " + ".join(kk["kernel"] for kk in kernels), "ms": round(k_ms, 3), "algorithmic_bytes": alg_bytes,
