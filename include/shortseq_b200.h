@@ -187,6 +187,11 @@ int ssq_counter_last_pass_detail(ssq_counter *c, float *pack_scatter_ms, float *
  * receives the tuples per partition; first_idx may be NULL. */
 int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *lens,
                        uint64_t *counts, int64_t *first_idx, int64_t *part_counts);
+/* ssq_counter_merge for tuples that arrive as n_blocks consecutive blocks (block_counts[] on the HOST), each ordered by
+ * the same hash -- what an owner receives from the ranks of a multi-GPU merge: the blocks are walked in lockstep so that
+ * every table line is fetched once, not once per block. */
+int ssq_counter_merge_blocks(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
+                             const int64_t *block_counts, int n_blocks);
 /* Multi-GPU send side without an intermediate buffer (ShortSeq64 counters): part_counts[n_parts] (device) = tuples
  * per hash partition; then partition p's tuples are written to dst_words[p][0..], dst_lens[p][0..], dst_counts[p][0..]
  * -- device arrays of n_parts DEVICE pointers, each of which may point into another GPU's memory (opened with

@@ -27,6 +27,10 @@ def merge():
     _lib.lib().ssq_counter_clear(owner.handle); owner.merge(w, l, c)
 ms, _ = t(merge)
 print(f"merge of {len(l)} tuples into owner table cap={owner.capacity()}: {ms:.2f} ms -> {len(owner)} keys")
+def merge_b():
+    _lib.lib().ssq_counter_clear(owner.handle); owner.merge_raw(w.data_ptr(), l.data_ptr(), c.data_ptr(), len(l), block_counts=[len(l) // P] * P)
+ms, _ = t(merge_b)
+print(f"merge_blocks (lockstep over the {P} blocks): {ms:.2f} ms -> {len(owner)} keys")
 # shuffled order for comparison
 perm = torch.randperm(len(l), device="cuda")
 w2, l2, c2 = w[perm].contiguous(), l[perm].contiguous(), c[perm].contiguous()

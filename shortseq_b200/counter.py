@@ -74,10 +74,17 @@ class DeviceCounter:
         self.ctx.bind()
         _lib.check(_lib.lib().ssq_counter_clear(self.handle))
 
-    def merge_raw(self, words_ptr, lens_ptr, counts_ptr, n):
-        """merge() on raw device pointers (the receive buffers of distributed.PeerExchange)."""
+    def merge_raw(self, words_ptr, lens_ptr, counts_ptr, n, block_counts=None):
+        """merge() on raw device pointers (the receive buffers of distributed.PeerExchange).  block_counts: the tuples
+        are that many consecutive hash-ordered blocks (one per sending rank), merged in lockstep."""
         self.ctx.bind()
-        _lib.check(_lib.lib().ssq_counter_merge(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), int(n)))
+        if block_counts is None:
+            _lib.check(_lib.lib().ssq_counter_merge(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), int(n)))
+        else:
+            bc = np.ascontiguousarray(block_counts, dtype=np.int64)
+            assert int(bc.sum()) == int(n)
+            _lib.check(_lib.lib().ssq_counter_merge_blocks(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr),
+                                                          bc.ctypes.data, int(bc.size)))
         _batch.raise_for_report(self.ctx.sync())
 
     def export_counts(self, n_parts):

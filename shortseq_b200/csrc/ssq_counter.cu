@@ -64,13 +64,61 @@ __global__ void __launch_bounds__(kThreads) insert_kernel(TableView t, const u64
         u32 len = lens[i];
         u64 add = counts ? counts[i] : 1ull;
         bool is_new = false;
+        u64 slot = 0;
         if (!len_in_class(KLASS, len)) {
             atomicMin(&t.rep->first_bad_len, (u64)(index_base + i));
         } else if (add != 0) {
-            if constexpr (KLASS == SSQ_CLASS_64) insert64(t, words[i], len, add, is_new);
+            if constexpr (KLASS == SSQ_CLASS_64) slot = insert64(t, words[i], len, add, is_new, true);
             else insert192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], len, add, is_new);
         }
+        if constexpr (KLASS == SSQ_CLASS_64) add_region_counts(t, is_new, slot);
         my_new += is_new ? 1u : 0u;
+    }
+    block_add_new(t, my_new, s_new);
+}
+
+// Weighted insert of several region-ordered blocks of tuples (what an owner receives from the P ranks of a multi-GPU
+// merge).  Chunk q of Q takes the q-th Q-th of EVERY block, and a thread inserts the tuples at the same relative
+// position of all blocks back to back: the blocks are ordered by the same hash, so those tuples fall into the same
+// few table lines, which are then fetched from DRAM once instead of once per block.
+constexpr int kMaxMergeBlocks = 32;
+struct MergeBlocks {
+    int64_t off[kMaxMergeBlocks + 1];
+    int n;
+};
+
+template <int KLASS>
+__global__ void __launch_bounds__(kThreads) merge_blocks_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
+                                                                MergeBlocks mb, int64_t nchunks) {
+    __shared__ u32 s_new[kThreads / 32];
+    u32 my_new = 0;
+    for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
+        int64_t longest = 0;
+        for (int b = 0; b < mb.n; b++) {
+            const int64_t len = mb.off[b + 1] - mb.off[b];
+            const int64_t c = len * (q + 1) / nchunks - len * q / nchunks;
+            longest = c > longest ? c : longest;
+        }
+        for (int64_t r = threadIdx.x; r < longest; r += kThreads) {
+            for (int b = 0; b < mb.n; b++) {
+                const int64_t len = mb.off[b + 1] - mb.off[b];
+                const int64_t lo = len * q / nchunks, hi = len * (q + 1) / nchunks;
+                if (r >= hi - lo) continue;
+                const int64_t i = mb.off[b] + lo + r;
+                const u32 l = lens[i];
+                const u64 add = counts[i];
+                bool is_new = false;
+                u64 slot = 0;
+                if (!len_in_class(KLASS, l)) {
+                    atomicMin(&t.rep->first_bad_len, (u64)i);
+                } else if (add != 0) {
+                    if constexpr (KLASS == SSQ_CLASS_64) slot = insert64(t, words[i], l, add, is_new, true);
+                    else insert192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], l, add, is_new);
+                }
+                if constexpr (KLASS == SSQ_CLASS_64) add_region_counts(t, is_new, slot);
+                my_new += is_new ? 1u : 0u;
+            }
+        }
     }
     block_add_new(t, my_new, s_new);
 }
@@ -1232,6 +1280,31 @@ int ssq_counter_insert(ssq_counter *c, const uint64_t *words, const uint8_t *len
 int ssq_counter_merge(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts, int64_t n) {
     SSQ_ARG(n == 0 || counts != nullptr, "counts is NULL");
     return insert_common(c, words, lens, counts, n);
+}
+
+int ssq_counter_merge_blocks(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
+                             const int64_t *block_counts, int n_blocks) {
+    SSQ_ARG(c != nullptr && block_counts != nullptr && n_blocks >= 1, "bad arguments");
+    int64_t n = 0;
+    for (int b = 0; b < n_blocks; b++) { SSQ_ARG(block_counts[b] >= 0, "negative block size"); n += block_counts[b]; }
+    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr), "NULL buffer");
+    if (n == 0) return SSQ_OK;
+    if (n_blocks > kMaxMergeBlocks || c->expected_unique <= 0 || n < 65536)
+        return insert_common(c, words, lens, counts, n);            // plain weighted insert
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    MergeBlocks mb;
+    mb.n = n_blocks;
+    mb.off[0] = 0;
+    for (int b = 0; b < n_blocks; b++) mb.off[b + 1] = mb.off[b] + block_counts[b];
+    const int64_t nchunks = n / 4096 > 0 ? n / 4096 : 1;
+    const int grid = grid_for(ctx, nchunks, 4);
+    if (c->klass == SSQ_CLASS_64)
+        merge_blocks_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts, mb, nchunks);
+    else
+        merge_blocks_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts, mb, nchunks);
+    SSQ_LAUNCH_CHECK();
+    return finish_pass(c);
 }
 
 int ssq_counter_pack_count(ssq_counter *c, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,

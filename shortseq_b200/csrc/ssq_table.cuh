@@ -88,7 +88,8 @@ __device__ __forceinline__ u64 key64_of(u64 h2, u32 len) {
 }
 
 // Returns the slot index (or kNoIndex on overflow); is_new is set when this call created the key.
-__device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 key, u64 add, bool &is_new) {
+// defer_region: the caller adds the new key to region_count itself (warp-aggregated, see add_region_counts)
+__device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 key, u64 add, bool &is_new, bool defer_region = false) {
     const u32 rmask = (1u << t.log2_region) - 1;
     const u64 home = h2 >> (64 - t.log2_cap);
     const u64 base = home & ~(u64)rmask;
@@ -102,7 +103,7 @@ __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 k
             k = atomicCAS(p, 0ull, key);
             if (k == 0) {
                 red_add_u64(p + 1, add);
-                red_add_u32(t.region_count + (slot >> t.log2_region), 1u);
+                if (!defer_region) red_add_u32(t.region_count + (slot >> t.log2_region), 1u);
                 is_new = true;
                 return slot;
             }
@@ -114,9 +115,19 @@ __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 k
     return kNoIndex;
 }
 
-__device__ __forceinline__ u64 insert64(const TableView &t, u64 word, u32 len, u64 add, bool &is_new) {
+__device__ __forceinline__ u64 insert64(const TableView &t, u64 word, u32 len, u64 add, bool &is_new, bool defer_region = false) {
     u64 h2 = rotl64(mix64(word), t.rot);
-    return insert64_hashed(t, h2, key64_of(h2, len), add, is_new);
+    return insert64_hashed(t, h2, key64_of(h2, len), add, is_new, defer_region);
+}
+
+// Region occupancy update for the lanes of a warp that just created keys (slot = their slots): lanes whose keys fell
+// into the same region send ONE add.  Hash-ordered input puts a whole warp into one or two regions, and same-address
+// atomics serialise in L2.  Call with the warp's active lanes converged.
+__device__ __forceinline__ void add_region_counts(const TableView &t, bool is_new, u64 slot) {
+    const unsigned act = __activemask();
+    const u32 region = is_new ? (u32)(slot >> t.log2_region) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(act, region);
+    if (is_new && (threadIdx.x & 31) == (u32)(__ffs(peers) - 1)) red_add_u32(t.region_count + region, (u32)__popc(peers));
 }
 
 __device__ __forceinline__ u64 find64(const TableView &t, u64 word, u32 len) {

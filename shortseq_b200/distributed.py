@@ -172,7 +172,7 @@ def merge_peer(local, owner, exchange, group=None):
     torch.cuda.synchronize(local.ctx.device)                            # my stores have landed ...
     dist.barrier(group)                                                 # ... and so have everyone else's
     t0 = _tick("export = exchange (peer stores)", t0, local.ctx)
-    owner.merge_raw(exchange.mine[0], exchange.mine[1], exchange.mine[2], int(m[:, rank].sum()))
+    owner.merge_raw(exchange.mine[0], exchange.mine[1], exchange.mine[2], int(m[:, rank].sum()), block_counts=m[:, rank])
     _tick("merge into owner table", t0, local.ctx)
     return owner
 

@@ -424,6 +424,31 @@ def test_counter_deferred_192(sq, oracle, skew):
 
 
 @pytest.mark.parametrize("klass", [0, 1])
+def test_counter_merge_blocks(sq, oracle, klass):
+    """ssq_counter_merge_blocks: hash-ordered blocks of (key, count) tuples from several counters merged in lockstep
+    equal the counts of all their reads together."""
+    import torch
+    lo, hi = (10, 32) if klass == 0 else (33, 96)
+    batches = [sq.synth_reads(120_000 + 7_000 * j, 30_000, lo, hi, seed=0x5EED0071, first_read=1_000_000 * j) for j in range(3)]
+    expect = {}
+    ws, ls, cs, sizes = [], [], [], []
+    for b in batches:
+        _, d = _oracle_counts_of_batch(oracle, b, klass)
+        for k, v in d.items():
+            expect[k] = expect.get(k, 0) + v
+        ctr = sq.DeviceCounter(klass, expected_unique=40_000)
+        ctr.pack_count(b)
+        keys, counts, _, _ = ctr.export(1)
+        ws.append(keys.words); ls.append(keys.lens); cs.append(counts); sizes.append(len(keys))
+    w, l, c = torch.cat(ws).contiguous(), torch.cat(ls).contiguous(), torch.cat(cs).contiguous()
+    owner = sq.DeviceCounter(klass, expected_unique=60_000)
+    owner.merge_raw(w.data_ptr(), l.data_ptr(), c.data_ptr(), int(l.numel()), block_counts=sizes)
+    keys, counts, _, _ = owner.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+
+
+@pytest.mark.parametrize("klass", [0, 1])
 def test_counter_deferred_tight_segments(sq, oracle, klass, monkeypatch):
     """Partition segments sized with no slack at all: about half of them overflow by a few keys, so every way a segment
     can end (full lines up to the cap, a partial last line that fits or does not) occurs; the excess is inserted
