@@ -187,11 +187,20 @@ int ssq_counter_last_pass_detail(ssq_counter *c, float *pack_scatter_ms, float *
  * receives the tuples per partition; first_idx may be NULL. */
 int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *lens,
                        uint64_t *counts, int64_t *first_idx, int64_t *part_counts);
-/* ssq_counter_merge for tuples that arrive as n_blocks consecutive blocks (block_counts[] on the HOST), each ordered by
- * the same hash -- what an owner receives from the ranks of a multi-GPU merge: the blocks are walked in lockstep so that
- * every table line is fetched once, not once per block. */
-int ssq_counter_merge_blocks(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
-                             const int64_t *block_counts, int n_blocks);
+/* Region-aligned ssq_counter_merge for ShortSeq64 owner tables of a multi-GPU merge.  The tuples are n_blocks consecutive
+ * blocks (block_counts[] on the HOST), one per sending rank, each in the order ssq_counter_export_to wrote it; block b
+ * comes from a table of block_regions[b]
+ * regions (ssq_counter_regions of the sender, divided by the number of owners) and region_bases + b * rb_stride holds
+ * the sender's exclusive scan of its region sizes for this owner (ssq_counter_export_region_bases; block_regions[b] + 1
+ * entries).  Every owner region is counted in shared memory from one contiguous range of every block: one pass, no
+ * global atomics.  Falls back to the plain weighted insert when the region grids do not nest. */
+int ssq_counter_regions(ssq_counter *c, int64_t *n_regions);
+int ssq_counter_merge_regions(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
+                              const int64_t *block_counts, const int64_t *block_regions, int n_blocks,
+                              const int64_t *region_bases, int64_t rb_stride);
+/* dst[p] (device table of n_parts DEVICE pointers, peer memory allowed) receives regions/n_parts + 1 offsets: where each of
+ * partition p's regions starts inside the block ssq_counter_export_to sends to p. */
+int ssq_counter_export_region_bases(ssq_counter *c, int n_parts, int64_t *const *dst);
 /* Multi-GPU send side without an intermediate buffer (ShortSeq64 counters): part_counts[n_parts] (device) = tuples
  * per hash partition; then partition p's tuples are written to dst_words[p][0..], dst_lens[p][0..], dst_counts[p][0..]
  * -- device arrays of n_parts DEVICE pointers, each of which may point into another GPU's memory (opened with

@@ -21,16 +21,34 @@ parts = parts.cpu().numpy()
 sl = slice(0, int(parts[0]))
 w = keys.words[sl].repeat(P); l = keys.lens[sl].repeat(P); c = counts[sl].repeat(P)
 rot = P.bit_length() - 1
-owner = sq.DeviceCounter(0, expected_unique=2 * u // P, hash_rot=rot)
+owner = sq.DeviceCounter(0, expected_unique=int(1.1 * u / P) + 1024, hash_rot=rot)   # like bench.py
 from shortseq_b200 import _lib
 def merge():
     _lib.lib().ssq_counter_clear(owner.handle); owner.merge(w, l, c)
 ms, _ = t(merge)
 print(f"merge of {len(l)} tuples into owner table cap={owner.capacity()}: {ms:.2f} ms -> {len(owner)} keys")
-def merge_b():
-    _lib.lib().ssq_counter_clear(owner.handle); owner.merge_raw(w.data_ptr(), l.data_ptr(), c.data_ptr(), len(l), block_counts=[len(l) // P] * P)
-ms, _ = t(merge_b)
-print(f"merge_blocks (lockstep over the {P} blocks): {ms:.2f} ms -> {len(owner)} keys")
+# region-aligned merge: P senders = P exports of the local table's partition 0 with their region offsets
+import numpy as np
+per_owner = local.regions() // P
+n0 = int(parts[0])
+W = torch.empty(P * n0, dtype=torch.int64, device="cuda"); L = torch.empty(P * n0, dtype=torch.uint8, device="cuda"); Cn = torch.empty(P * n0, dtype=torch.int64, device="cuda")
+rb = torch.empty((P, per_owner + 1), dtype=torch.int64, device="cuda")
+big = int(parts.max())
+dw = torch.empty(big, dtype=torch.int64, device="cuda"); dl = torch.empty(big, dtype=torch.uint8, device="cuda"); dc = torch.empty(big, dtype=torch.int64, device="cuda"); drb = torch.empty(per_owner + 1, dtype=torch.int64, device="cuda")
+for s_ in range(P):
+    tb = np.empty((3, P), dtype=np.int64)
+    for p_ in range(P):
+        tb[0, p_] = W.data_ptr() + 8 * s_ * n0 if p_ == 0 else dw.data_ptr()
+        tb[1, p_] = L.data_ptr() + s_ * n0 if p_ == 0 else dl.data_ptr()
+        tb[2, p_] = Cn.data_ptr() + 8 * s_ * n0 if p_ == 0 else dc.data_ptr()
+    local.export_to(P, torch.from_numpy(tb).cuda())
+    local.export_region_bases(P, torch.from_numpy(np.array([rb[s_].data_ptr() if p_ == 0 else drb.data_ptr() for p_ in range(P)], dtype=np.int64)).cuda())
+torch.cuda.synchronize()
+def merge_r():
+    _lib.lib().ssq_counter_clear(owner.handle)
+    owner.merge_regions_raw(W.data_ptr(), L.data_ptr(), Cn.data_ptr(), P * n0, [n0] * P, [per_owner] * P, rb.data_ptr(), per_owner + 1)
+ms, _ = t(merge_r)
+print(f"merge_regions (shared-memory, region by region): {ms:.2f} ms -> {len(owner)} keys")
 # shuffled order for comparison
 perm = torch.randperm(len(l), device="cuda")
 w2, l2, c2 = w[perm].contiguous(), l[perm].contiguous(), c[perm].contiguous()

@@ -65,7 +65,9 @@ PROTOTYPES = {
     "ssq_counter_size": (_int, [_p, C.POINTER(_i64)]),
     "ssq_counter_capacity": (_int, [_p, C.POINTER(_i64)]),
     "ssq_counter_last_pass_ms": (_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-    "ssq_counter_merge_blocks": (_int, [_p, _p, _p, _p, _p, _int]),
+    "ssq_counter_regions": (_int, [_p, C.POINTER(_i64)]),
+    "ssq_counter_merge_regions": (_int, [_p, _p, _p, _p, _p, _p, _int, _p, _i64]),
+    "ssq_counter_export_region_bases": (_int, [_p, _int, _p]),
     "ssq_counter_export_counts": (_int, [_p, _int, _p]),
     "ssq_counter_export_to": (_int, [_p, _int, _int, _p, _p, _p]),
     "ssq_ipc_get_handle": (_int, [_p, _p, _p]),

@@ -74,17 +74,33 @@ class DeviceCounter:
         self.ctx.bind()
         _lib.check(_lib.lib().ssq_counter_clear(self.handle))
 
-    def merge_raw(self, words_ptr, lens_ptr, counts_ptr, n, block_counts=None):
-        """merge() on raw device pointers (the receive buffers of distributed.PeerExchange).  block_counts: the tuples
-        are that many consecutive hash-ordered blocks (one per sending rank), merged in lockstep."""
+    def merge_raw(self, words_ptr, lens_ptr, counts_ptr, n):
+        """merge() on raw device pointers (the receive buffers of distributed.PeerExchange)."""
         self.ctx.bind()
-        if block_counts is None:
-            _lib.check(_lib.lib().ssq_counter_merge(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), int(n)))
-        else:
-            bc = np.ascontiguousarray(block_counts, dtype=np.int64)
-            assert int(bc.sum()) == int(n)
-            _lib.check(_lib.lib().ssq_counter_merge_blocks(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr),
-                                                          bc.ctypes.data, int(bc.size)))
+        _lib.check(_lib.lib().ssq_counter_merge(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), int(n)))
+        _batch.raise_for_report(self.ctx.sync())
+
+    def regions(self):
+        """Number of table regions (ShortSeq64 counters; 0 otherwise)."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().ssq_counter_regions(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def export_region_bases(self, n_parts, dst_table):
+        """Write, for every partition p, the offsets of its regions inside the block export_to sends to p to the device
+        pointer dst_table[p] (int64 device tensor [n_parts]; the pointers may be peer memory)."""
+        assert dst_table.dtype == torch.int64 and dst_table.numel() == n_parts and dst_table.is_contiguous()
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_export_region_bases(self.handle, int(n_parts), dst_table.data_ptr()))
+
+    def merge_regions_raw(self, words_ptr, lens_ptr, counts_ptr, n, block_counts, block_regions, region_bases_ptr, rb_stride):
+        """Region-aligned merge of hash-ordered blocks (see ssq_counter_merge_regions)."""
+        bc = np.ascontiguousarray(block_counts, dtype=np.int64)
+        br = np.ascontiguousarray(block_regions, dtype=np.int64)
+        assert int(bc.sum()) == int(n) and bc.size == br.size
+        self.ctx.bind()
+        _lib.check(_lib.lib().ssq_counter_merge_regions(self.handle, int(words_ptr), int(lens_ptr), int(counts_ptr), bc.ctypes.data,
+                                                       br.ctypes.data, int(bc.size), int(region_bases_ptr), int(rb_stride)))
         _batch.raise_for_report(self.ctx.sync())
 
     def export_counts(self, n_parts):

@@ -77,50 +77,107 @@ __global__ void __launch_bounds__(kThreads) insert_kernel(TableView t, const u64
     block_add_new(t, my_new, s_new);
 }
 
-// Weighted insert of several region-ordered blocks of tuples (what an owner receives from the P ranks of a multi-GPU
-// merge).  Chunk q of Q takes the q-th Q-th of EVERY block, and a thread inserts the tuples at the same relative
-// position of all blocks back to back: the blocks are ordered by the same hash, so those tuples fall into the same
-// few table lines, which are then fetched from DRAM once instead of once per block.
 constexpr int kMaxMergeBlocks = 32;
-struct MergeBlocks {
-    int64_t off[kMaxMergeBlocks + 1];
+
+// Region-aligned weighted merge (ShortSeq64 owner tables of a multi-GPU merge).  Every sender's block is ordered by
+// ITS table regions, and it also sent the exclusive scan of its region sizes (region_bases).  An owner region is a
+// whole number of consecutive sender regions, so the tuples that belong to one owner region are one contiguous range
+// of every block: a CTA loads the owner region into shared memory, adds those ranges with shared-memory atomics and
+// writes the region back -- one pass, no global atomics (the weighted global insert it replaces is bound by L2
+// atomic throughput).
+struct MergeRegions {
+    int64_t off[kMaxMergeBlocks + 1];      // first tuple of every block
+    int ratio_log2[kMaxMergeBlocks];       // log2(sender regions per owner region)
     int n;
+    int64_t rb_stride;                     // int64 entries between the region_bases of consecutive blocks
 };
 
-template <int KLASS>
-__global__ void __launch_bounds__(kThreads) merge_blocks_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
-                                                                MergeBlocks mb, int64_t nchunks) {
+__global__ void __launch_bounds__(kThreads, 3) merge_regions_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
+                                                                    const int64_t *region_bases, MergeRegions mr) {
+    extern __shared__ __align__(16) u64 dyn_region[];
     __shared__ u32 s_new[kThreads / 32];
-    u32 my_new = 0;
-    for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
-        int64_t longest = 0;
-        for (int b = 0; b < mb.n; b++) {
-            const int64_t len = mb.off[b + 1] - mb.off[b];
-            const int64_t c = len * (q + 1) / nchunks - len * q / nchunks;
-            longest = c > longest ? c : longest;
-        }
-        for (int64_t r = threadIdx.x; r < longest; r += kThreads) {
-            for (int b = 0; b < mb.n; b++) {
-                const int64_t len = mb.off[b + 1] - mb.off[b];
-                const int64_t lo = len * q / nchunks, hi = len * (q + 1) / nchunks;
-                if (r >= hi - lo) continue;
-                const int64_t i = mb.off[b] + lo + r;
-                const u32 l = lens[i];
-                const u64 add = counts[i];
-                bool is_new = false;
-                u64 slot = 0;
-                if (!len_in_class(KLASS, l)) {
-                    atomicMin(&t.rep->first_bad_len, (u64)i);
-                } else if (add != 0) {
-                    if constexpr (KLASS == SSQ_CLASS_64) slot = insert64(t, words[i], l, add, is_new, true);
-                    else insert192(t, words[3 * i], words[3 * i + 1], words[3 * i + 2], l, add, is_new);
+    const u32 R = 1u << t.log2_region, rmask = R - 1;
+    u64 *ks = dyn_region, *cs = dyn_region + R;
+    const u32 region = blockIdx.x;
+    ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
+    const bool was_empty = t.region_count[region] == 0;
+    for (u32 i = threadIdx.x; i < R; i += kThreads) {
+        const ulonglong2 v = was_empty ? make_ulonglong2(0ull, 0ull) : gslots[i];
+        ks[i] = v.x;
+        cs[i] = v.y;
+    }
+    __shared__ int64_t s_lo[kMaxMergeBlocks], s_hi[kMaxMergeBlocks];
+    if ((int)threadIdx.x < mr.n) {                          // this region's tuple range in every block (loads overlap the region load)
+        const int b = threadIdx.x;
+        const int64_t *rb = region_bases + (size_t)b * mr.rb_stride;
+        s_lo[b] = mr.off[b] + rb[(size_t)region << mr.ratio_log2[b]];
+        s_hi[b] = mr.off[b] + rb[((size_t)region + 1) << mr.ratio_log2[b]];
+    }
+    __syncthreads();
+    const int off_shift = 64 - t.log2_cap;
+    u32 my_new = 0, overflow = 0, bad = 0, touched = 0;
+    for (int b = 0; b < mr.n; b++) {
+        const int64_t lo = s_lo[b], hi = s_hi[b];
+        constexpr int kU = 4;                                      // tuples per thread in flight
+        for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)kU * kThreads) {
+            u64 wv[kU], av[kU];
+            u32 lv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int64_t i = i0 + (int64_t)u * kThreads;
+                lv[u] = 0xFFFFFFFFu;
+                if (i < hi) { wv[u] = words[i]; av[u] = counts[i]; lv[u] = lens[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                if (lv[u] == 0xFFFFFFFFu) continue;
+                const u32 len = lv[u];
+                const u64 add = av[u];
+                const u64 h2 = rotl64(mix64(wv[u]), t.rot);
+                if (len > 32 || (u32)((h2 >> off_shift) >> t.log2_region) != region) { ++bad; continue; }   // not this region's tuple
+                const u64 key = key64_of(h2, len);
+                u32 off = (u32)(h2 >> off_shift) & rmask;
+                u32 left = R;
+                touched = 1;
+                for (;;) {
+                    u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
+                    if (cur == 0) {
+                        cur = atomicCAS(ks + off, 0ull, key);
+                        if (cur == 0) { ++my_new; cur = key; }
+                    }
+                    if (cur == key) { atomicAdd(cs + off, add); break; }
+                    off = (off + 1) & rmask;
+                    if (--left == 0) { ++overflow; break; }
                 }
-                if constexpr (KLASS == SSQ_CLASS_64) add_region_counts(t, is_new, slot);
-                my_new += is_new ? 1u : 0u;
+                __syncwarp(__activemask());
             }
         }
     }
-    block_add_new(t, my_new, s_new);
+    const int any = __syncthreads_or((int)touched);
+    if (any)
+        for (u32 i = threadIdx.x; i < R; i += kThreads) gslots[i] = make_ulonglong2(ks[i], cs[i]);
+    if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
+    if (bad) atomicMin(&t.rep->first_bad_len, 0ull);        // inconsistent blocks: surfaces as an error, never as wrong counts
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+    if ((threadIdx.x & 31) == 0) s_new[threadIdx.x >> 5] = my_new;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int k = 0; k < kThreads / 32; k++) tot += s_new[k];
+        if (tot) { atomicAdd(t.size, (u64)tot); red_add_u32(t.region_count + region, tot); }
+    }
+}
+
+// dst[p][j] = region_base[p * R + j] - region_base[p * R], j = 0..R (R = regions per partition): what owner p needs to find
+// its regions' tuples inside the block this rank sends it
+__global__ void export_region_bases_kernel(const int64_t *region_base, int log2_regions, int log2_parts, int64_t *const *dst) {
+    const int64_t per = (int64_t)1 << (log2_regions - log2_parts);
+    const int64_t total = (per + 1) << log2_parts;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / (per + 1), j = i - p * (per + 1);
+        dst[p][j] = region_base[p * per + j] - region_base[p * per];
+    }
 }
 
 template <int KLASS>
@@ -1282,29 +1339,60 @@ int ssq_counter_merge(ssq_counter *c, const uint64_t *words, const uint8_t *lens
     return insert_common(c, words, lens, counts, n);
 }
 
-int ssq_counter_merge_blocks(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
-                             const int64_t *block_counts, int n_blocks) {
-    SSQ_ARG(c != nullptr && block_counts != nullptr && n_blocks >= 1, "bad arguments");
+int ssq_counter_regions(ssq_counter *c, int64_t *n_regions) {
+    SSQ_ARG(c != nullptr && n_regions != nullptr, "NULL argument");
+    *n_regions = c->klass == SSQ_CLASS_64 ? (int64_t)1 << (c->log2_cap - region_bits_for(c->log2_cap)) : 0;
+    return SSQ_OK;
+}
+
+int ssq_counter_merge_regions(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
+                              const int64_t *block_counts, const int64_t *block_regions, int n_blocks,
+                              const int64_t *region_bases, int64_t rb_stride) {
+    SSQ_ARG(c != nullptr && block_counts != nullptr && block_regions != nullptr && n_blocks >= 1, "bad arguments");
     int64_t n = 0;
     for (int b = 0; b < n_blocks; b++) { SSQ_ARG(block_counts[b] >= 0, "negative block size"); n += block_counts[b]; }
-    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr), "NULL buffer");
+    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr && region_bases != nullptr), "NULL buffer");
     if (n == 0) return SSQ_OK;
-    if (n_blocks > kMaxMergeBlocks || c->expected_unique <= 0 || n < 65536)
-        return insert_common(c, words, lens, counts, n);            // plain weighted insert
+    const int lr = region_bits_for(c->log2_cap);
+    const int64_t my_regions = (int64_t)1 << (c->log2_cap - lr);
+    bool ok = c->klass == SSQ_CLASS_64 && c->expected_unique > 0 && n_blocks <= kMaxMergeBlocks && lr <= 12;
+    MergeRegions mr;
+    mr.n = n_blocks;
+    mr.rb_stride = rb_stride;
+    mr.off[0] = 0;
+    for (int b = 0; b < n_blocks && ok; b++) {
+        mr.off[b + 1] = mr.off[b] + block_counts[b];
+        int r = 0;
+        while (((int64_t)my_regions << r) < block_regions[b]) r++;
+        ok = ((int64_t)my_regions << r) == block_regions[b] && block_regions[b] + 1 <= rb_stride;   // a whole number of sender regions per owner region
+        mr.ratio_log2[b] = r;
+    }
+    if (!ok) return insert_common(c, words, lens, counts, n);     // the region grids do not nest: plain weighted insert
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
-    MergeBlocks mb;
-    mb.n = n_blocks;
-    mb.off[0] = 0;
-    for (int b = 0; b < n_blocks; b++) mb.off[b + 1] = mb.off[b] + block_counts[b];
-    const int64_t nchunks = n / 4096 > 0 ? n / 4096 : 1;
-    const int grid = grid_for(ctx, nchunks, 4);
-    if (c->klass == SSQ_CLASS_64)
-        merge_blocks_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts, mb, nchunks);
-    else
-        merge_blocks_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts, mb, nchunks);
+    const size_t bytes = (size_t)16 << lr;
+    int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
+    if (rc) return rc;
+    merge_regions_kernel<<<(unsigned)my_regions, kThreads, bytes, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts,
+                                                                              region_bases, mr);
     SSQ_LAUNCH_CHECK();
     return finish_pass(c);
+}
+
+int ssq_counter_export_region_bases(ssq_counter *c, int n_parts, int64_t *const *dst) {
+    SSQ_ARG(c != nullptr && dst != nullptr, "NULL argument");
+    SSQ_ARG(n_parts >= 1 && n_parts <= kMaxParts && (n_parts & (n_parts - 1)) == 0, "n_parts must be a power of two <= 256");
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    if (!region_export_ok(c, log2_parts)) { set_error("ssq_counter_export_region_bases needs a ShortSeq64 counter with at least n_parts regions"); return SSQ_ERR_ARG; }
+    DeviceGuard g(c->ctx->device);
+    int rc = scan_regions(c);
+    if (rc) return rc;
+    const int log2_regions = c->log2_cap - region_bits_for(c->log2_cap);
+    export_region_bases_kernel<<<grid_for(c->ctx, (((int64_t)1 << log2_regions) + n_parts + 255) / 256, 4), 256, 0, c->ctx->stream>>>(
+        c->region_base, log2_regions, log2_parts, dst);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
 }
 
 int ssq_counter_pack_count(ssq_counter *c, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *offsets,

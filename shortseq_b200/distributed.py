@@ -92,9 +92,10 @@ class PeerExchange:
     def __init__(self, ctx, group=None):
         self.ctx, self.group = ctx, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.cap = 0
-        self.mine = [0, 0, 0]                       # words / lens / counts receive buffers (device pointers)
-        self.peer = [[0] * self.world for _ in range(3)]
+        self.cap = 0                                # tuples the receive buffers hold
+        self.rb_cap = 0                             # sender regions per owner the region-base buffer holds
+        self.mine = [0, 0, 0, 0]                    # words / lens / counts / region-base receive buffers (device pointers)
+        self.peer = [[0] * self.world for _ in range(4)]
         self._opened = []
 
     def _release(self):
@@ -106,8 +107,9 @@ class PeerExchange:
         for p in self.mine:
             if p:
                 lib.ssq_free(h, p)
-        self.mine = [0, 0, 0]
+        self.mine = [0, 0, 0, 0]
         self.cap = 0
+        self.rb_cap = 0
 
     def close(self):
         """Collective: unmap the peers' buffers, then free this rank's."""
@@ -115,9 +117,10 @@ class PeerExchange:
         dist.barrier(self.group)
         self._release()
 
-    def ensure(self, need):
-        """Collective (every rank passes the same `need`): receive buffers for at least `need` tuples."""
-        if need <= self.cap:
+    def ensure(self, need, need_regions=0):
+        """Collective (every rank passes the same arguments): receive buffers for at least `need` tuples and, per
+        sending rank, the offsets of `need_regions` sender regions."""
+        if need <= self.cap and need_regions <= self.rb_cap:
             return
         import ctypes as C
         from . import _lib
@@ -126,10 +129,11 @@ class PeerExchange:
         dist.barrier(self.group)                   # nobody is still writing into, or reading from, the old buffers
         self._release()
         cap = int(need * 1.25) + 1024
-        handles = torch.zeros(3 * 64, dtype=torch.uint8)
-        for k, elem in enumerate((8, 1, 8)):
+        rb_cap = max(int(need_regions), 1)
+        handles = torch.zeros(4 * 64, dtype=torch.uint8)
+        for k, nbytes in enumerate((8 * cap, cap, 8 * cap, 8 * self.world * (rb_cap + 1))):
             p = C.c_void_p()
-            _lib.check(lib.ssq_malloc(h, cap * elem, C.byref(p)))
+            _lib.check(lib.ssq_malloc(h, nbytes, C.byref(p)))
             self.mine[k] = p.value
             hb = (C.c_ubyte * 64)()
             _lib.check(lib.ssq_ipc_get_handle(h, p, hb))
@@ -139,7 +143,7 @@ class PeerExchange:
         dist.all_gather(gathered, mine, group=self.group)
         for r in range(self.world):
             hr = gathered[r].cpu().numpy().tobytes()
-            for k in range(3):
+            for k in range(4):
                 if r == self.rank:
                     self.peer[k][r] = self.mine[k]
                 else:
@@ -148,6 +152,7 @@ class PeerExchange:
                     self.peer[k][r] = p.value
                     self._opened.append(p.value)
         self.cap = cap
+        self.rb_cap = rb_cap
 
 
 def merge_peer(local, owner, exchange, group=None):
@@ -157,22 +162,29 @@ def merge_peer(local, owner, exchange, group=None):
     world, rank = exchange.world, exchange.rank
     t0 = _tick("start", time.perf_counter(), local.ctx) if _TIMING else 0.0
     parts = local.export_counts(world)                                  # tuples this rank holds for every owner
-    matrix = [torch.empty_like(parts) for _ in range(world)]
-    dist.all_gather(matrix, parts, group=group)                         # matrix[src][dst]
-    m = torch.stack(matrix).cpu().numpy()                               # host sync: every rank has entered this merge
+    mine = torch.cat([parts, torch.tensor([local.regions()], dtype=torch.int64, device=parts.device)])
+    matrix = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(matrix, mine, group=group)                          # matrix[src] = tuples per dst, then src's region count
+    mm = torch.stack(matrix).cpu().numpy()                              # host sync: every rank has entered this merge
+    m, regions = mm[:, :world], mm[:, world] // world                   # sender regions per owner
     t0 = _tick("size matrix", t0, local.ctx)
-    exchange.ensure(int(m.sum(axis=0).max()))
+    exchange.ensure(int(m.sum(axis=0).max()), int(regions.max()))
     import numpy as np
     before = m[:rank].sum(axis=0) if rank else np.zeros(world, dtype=np.int64)   # where my block starts in each owner's buffer
-    table = np.empty((3, world), dtype=np.int64)
+    table = np.empty((4, world), dtype=np.int64)
     for k, elem in enumerate((8, 1, 8)):
         table[k] = [exchange.peer[k][d] + elem * int(before[d]) for d in range(world)]
+    rb_stride = exchange.rb_cap + 1
+    table[3] = [exchange.peer[3][d] + 8 * rank * rb_stride for d in range(world)]
+    dtable = torch.from_numpy(table).to(local.ctx.device)
     # rank r starts with owner r + 1: at any moment every owner receives from one sender
-    local.export_to(world, torch.from_numpy(table).to(local.ctx.device), first_part=(rank + 1) % world)
+    local.export_to(world, dtable[:3].contiguous(), first_part=(rank + 1) % world)
+    local.export_region_bases(world, dtable[3].contiguous())
     torch.cuda.synchronize(local.ctx.device)                            # my stores have landed ...
     dist.barrier(group)                                                 # ... and so have everyone else's
     t0 = _tick("export = exchange (peer stores)", t0, local.ctx)
-    owner.merge_raw(exchange.mine[0], exchange.mine[1], exchange.mine[2], int(m[:, rank].sum()), block_counts=m[:, rank])
+    owner.merge_regions_raw(exchange.mine[0], exchange.mine[1], exchange.mine[2], int(m[:, rank].sum()), m[:, rank], regions,
+                            exchange.mine[3], rb_stride)
     _tick("merge into owner table", t0, local.ctx)
     return owner
 

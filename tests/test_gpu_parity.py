@@ -423,10 +423,66 @@ def test_counter_deferred_192(sq, oracle, skew):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
 
 
+@pytest.mark.parametrize("owner_unique", [400_000, 250_000])
+def test_counter_merge_regions(sq, oracle, owner_unique):
+    """The owner side of the multi-GPU merge on one GPU: P sender tables export one owner's share (tuples + region
+    offsets) into receive buffers; ssq_counter_merge_regions counts them region by region in shared memory.
+    owner_unique 400k: owner regions = sender regions per owner; 250k: two sender regions per owner region."""
+    import torch
+    from shortseq_b200 import hashing
+    P, me = 4, 1
+    dev = None
+    senders, expect = [], {}
+    for s_ in range(P):
+        b = sq.synth_reads(900_000, 1_200_000, 14, 32, seed=0x5EED0081, first_read=900_000 * s_)
+        (ow, ol), d = _oracle_counts_of_batch(oracle, b, 0)
+        for k, v in d.items():
+            expect[k] = expect.get(k, 0) + v
+        c = sq.DeviceCounter(0, expected_unique=1_500_000)
+        c.pack_count(b)
+        senders.append(c)
+        dev = c.ctx.device
+    assert senders[0].capacity() == 1 << 22 and senders[0].regions() == 1024
+    sizes = [c.export_counts(P).cpu().numpy() for c in senders]
+    per_owner = senders[0].regions() // P
+    total = int(sum(sz[me] for sz in sizes))
+    words = torch.empty(total, dtype=torch.int64, device=dev)
+    lens = torch.empty(total, dtype=torch.uint8, device=dev)
+    counts = torch.empty(total, dtype=torch.int64, device=dev)
+    rb = torch.empty((P, per_owner + 1), dtype=torch.int64, device=dev)
+    big = int(max(sz.max() for sz in sizes))
+    dump_w = torch.empty(big, dtype=torch.int64, device=dev); dump_l = torch.empty(big, dtype=torch.uint8, device=dev)
+    dump_c = torch.empty(big, dtype=torch.int64, device=dev); dump_rb = torch.empty(per_owner + 1, dtype=torch.int64, device=dev)
+    at = 0
+    for s_, c in enumerate(senders):
+        table = np.empty((3, P), dtype=np.int64)
+        for p_ in range(P):
+            mine = p_ == me
+            table[0, p_] = words.data_ptr() + 8 * at if mine else dump_w.data_ptr()
+            table[1, p_] = lens.data_ptr() + at if mine else dump_l.data_ptr()
+            table[2, p_] = counts.data_ptr() + 8 * at if mine else dump_c.data_ptr()
+        c.export_to(P, torch.from_numpy(table).to(dev), first_part=(s_ + 1) % P)
+        rbt = np.array([rb[s_].data_ptr() if p_ == me else dump_rb.data_ptr() for p_ in range(P)], dtype=np.int64)
+        c.export_region_bases(P, torch.from_numpy(rbt).to(dev))
+        at += int(sizes[s_][me])
+    torch.cuda.synchronize()
+    owner = sq.DeviceCounter(0, expected_unique=owner_unique, hash_rot=2)
+    owner.merge_regions_raw(words.data_ptr(), lens.data_ptr(), counts.data_ptr(), total, [int(sz[me]) for sz in sizes],
+                            [per_owner] * P, rb.data_ptr(), per_owner + 1)
+    keys, cnt, _, _ = owner.export(1)
+    kw, kl, _ = keys.to_host()
+    got = counter_dict(kw, kl, cnt.cpu().numpy())
+    ew = np.array([k[1][0] for k in expect], dtype=np.uint64)
+    el = np.array([k[0] for k in expect], dtype=np.uint8)
+    own = hashing.owner_rank(ew, el, 0, P)
+    mine_expect = {k: v for (k, v), o in zip(expect.items(), own) if o == me}
+    assert len(owner) == len(mine_expect)
+    assert got == mine_expect
+
+
 @pytest.mark.parametrize("klass", [0, 1])
-def test_counter_merge_blocks(sq, oracle, klass):
-    """ssq_counter_merge_blocks: hash-ordered blocks of (key, count) tuples from several counters merged in lockstep
-    equal the counts of all their reads together."""
+def test_counter_merge_exports(sq, oracle, klass):
+    """ssq_counter_merge of the concatenated exports of several counters equals the counts of all their reads."""
     import torch
     lo, hi = (10, 32) if klass == 0 else (33, 96)
     batches = [sq.synth_reads(120_000 + 7_000 * j, 30_000, lo, hi, seed=0x5EED0071, first_read=1_000_000 * j) for j in range(3)]
@@ -442,7 +498,7 @@ def test_counter_merge_blocks(sq, oracle, klass):
         ws.append(keys.words); ls.append(keys.lens); cs.append(counts); sizes.append(len(keys))
     w, l, c = torch.cat(ws).contiguous(), torch.cat(ls).contiguous(), torch.cat(cs).contiguous()
     owner = sq.DeviceCounter(klass, expected_unique=60_000)
-    owner.merge_raw(w.data_ptr(), l.data_ptr(), c.data_ptr(), int(l.numel()), block_counts=sizes)
+    owner.merge_raw(w.data_ptr(), l.data_ptr(), c.data_ptr(), int(l.numel()))
     keys, counts, _, _ = owner.export(1)
     kw, kl, _ = keys.to_host()
     assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
