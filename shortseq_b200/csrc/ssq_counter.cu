@@ -524,7 +524,10 @@ count_regions_kernel(TableView t, RegionParts rp) {
     __syncthreads();
     for (u32 i = threadIdx.x; i < R; i += THREADS) {
         const u32 d = ds[i];
-        if (d) gslots[i] = make_ulonglong2(ks[i], (was_empty ? 0ull : gslots[i].y) + d);
+        // a region that was empty is written whole (full, coalesced sectors; its slots are known to be zero otherwise);
+        // elsewhere only the touched slots, with the old count re-read from L2
+        if (was_empty) gslots[i] = make_ulonglong2(ks[i], (u64)d);
+        else if (d) gslots[i] = make_ulonglong2(ks[i], gslots[i].y + d);
     }
     if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
     // keys created in this region: table size and the region's occupancy
