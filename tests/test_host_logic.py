@@ -97,3 +97,33 @@ def test_owner_rank_partitions_evenly_and_by_full_key():
     assert (r1 != r2).mean() > 0.5            # length is part of the key
     assert int(hashing.mix64(np.uint64(0))) == int(O.lib().ssq_oracle_mix64(0))
     assert int(hashing.mix64(np.uint64(12345))) == int(O.lib().ssq_oracle_mix64(12345))
+
+
+def test_fastq_line_rule_matches_reference(tmp_path):
+    """The host restatement of the reference's FASTQ line rule (shortseq_b200.counter._fastq_reads_host: lines 2 mod 4,
+    last byte dropped, lines end at '\\n' only) -- the expectation the GPU ingest tests compare against -- agrees with the
+    unmodified reference's read_and_count_fastq (counter.pyx:57-71) when oracle/_ref is built."""
+    import collections
+    from oracle import ref as R
+    from shortseq_b200.counter import _fastq_reads_host
+    ref = R.load()
+    if ref is None:
+        pytest.skip("oracle/_ref (the built reference) is not available")
+    rng = np.random.default_rng(99)
+    recs = []
+    for i in range(3000):
+        L = int(rng.integers(1, 97))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L).tobytes())
+        qual = bytes(rng.integers(33, 74, size=L, dtype=np.uint8).tobytes())
+        if i % 5 == 0:
+            qual = b"@" + qual[1:]
+        recs += [b"@r%d" % i, seq, b"+", qual]
+    for tail in (b"\n", b"", b"\n@last\nACGTAC"):            # terminated, unterminated, truncated record (T9)
+        text = b"\n".join(recs) + tail
+        p = tmp_path / "x.fastq"
+        p.write_bytes(text)
+        mine = collections.OrderedDict()
+        for r in _fastq_reads_host(np.frombuffer(text, dtype=np.uint8)):
+            mine[r.decode()] = mine.get(r.decode(), 0) + 1
+        theirs = collections.OrderedDict((str(k), v) for k, v in ref.read_and_count_fastq(str(p)).items())
+        assert mine == theirs and list(mine) == list(theirs)
