@@ -6,10 +6,11 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- synthetic 32-nt reads -> ShortSeq64 pack + dedup
 count, 1e9 reads and 1e8 distinct sequences PER GPU (weak scaling; the generator of SURVEY section 8d).
-A step = one ShortSeqCounter construction over the whole resident batch: clear the table, fused
-pack+count kernel over all reads (packed words and lengths are written out), and for N > 1 the
-hash-partitioned all-to-all merge into per-rank owner tables; the step ends with the device->host read
-of the number of distinct keys.
+A step = one ShortSeqCounter construction over the whole resident batch: clear the table, the fused
+pack+count pass over all reads (pack + level-1 scatter, region scatter, shared-memory region count; packed
+words and lengths are written out), and for N > 1 the hash-partitioned exchange of the distinct keys (the export
+kernel stores each owner's share into that owner's memory over NVLink; --nccl-exchange: NCCL all-to-all) and the
+merge into per-rank owner tables; the step ends with the device->host read of the number of distinct keys.
 
   value     whole-job Gbases/s with the reads resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the host-buffer C-ABI call ssq_host_pack_count_lens: pinned host ASCII + one
