@@ -13,7 +13,7 @@ from . import _lib
 from . import batch as _batch
 from ._lib import CLASS_64, CLASS_192, CLASS_VAR
 from ._runtime import MSG_TOO_LONG, bad_base_message, context, gather_reads, ptr, words_to_numpy
-from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _box, _box_many
+from .short_seq import ShortSeq64, ShortSeq192, ShortSeqVar, _NoGC, _box, _box_many
 
 
 class DeviceCounter:
@@ -218,7 +218,8 @@ def _fill_in_order(dst, groups):
     if not objs:
         return
     order = np.argsort(np.concatenate(firsts), kind="stable").tolist()
-    dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
+    with _NoGC():
+        dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
 
 
 class ShortSeqCounter(dict):

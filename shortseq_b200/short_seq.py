@@ -153,6 +153,22 @@ def _box(klass, packed, length):
     return obj
 
 
+class _NoGC:
+    """Bulk creation of millions of small objects: the cyclic collector would rescan the growing heap over and over
+    (3x the time of the loop itself); none of these objects can be part of a cycle."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        if self._was:
+            import gc
+            gc.enable()
+        return False
+
+
 def _box_many(klass, words, lens):
     """Box a whole array of fixed-class keys: words uint64 ndarray [n] (ShortSeq64) or [n, 3] (ShortSeq192), lens
     ndarray [n] -> list of ShortSeq objects.  The per-object work is three slot stores; blocks, lengths and hashes are
@@ -162,16 +178,18 @@ def _box_many(klass, words, lens):
     first = w if w.ndim == 1 else w[:, 0]
     hashes = first.view(np.int64).copy()
     hashes[hashes == -1] = -2
-    packed = [(x,) for x in w.tolist()] if w.ndim == 1 else [tuple(r) for r in w.tolist()]
+    with _NoGC():
+        packed = [(x,) for x in w.tolist()] if w.ndim == 1 else [tuple(r) for r in w.tolist()]
     new = object.__new__
     out = []
     append = out.append
-    for p, l, h in zip(packed, np.asarray(lens).tolist(), hashes.tolist()):
-        o = new(cls)
-        o._packed = p
-        o._length = l
-        o._hash = h
-        append(o)
+    with _NoGC():
+        for p, l, h in zip(packed, np.asarray(lens).tolist(), hashes.tolist()):
+            o = new(cls)
+            o._packed = p
+            o._length = l
+            o._hash = h
+            append(o)
     return out
 
 
