@@ -102,10 +102,11 @@ def gather_reads(reads):
     (counter.pyx:27): a non-bytes element is a TypeError.
     """
     n = len(reads)
-    for r in reads:
-        if type(r) is not bytes:
-            raise TypeError(f"expected bytes, {type(r).__name__} found")
-    lens = np.fromiter((len(r) for r in reads), dtype=np.int64, count=n)
+    kinds = set(map(type, reads))                       # C-speed pass; the common case is {bytes}
+    if kinds - {bytes}:
+        bad = next(r for r in reads if type(r) is not bytes)
+        raise TypeError(f"expected bytes, {type(bad).__name__} found")
+    lens = np.fromiter(map(len, reads), dtype=np.int64, count=n)
     offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
     buf = np.frombuffer(b"".join(reads), dtype=np.uint8)
