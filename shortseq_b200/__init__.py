@@ -4,14 +4,15 @@ Same public names as the reference's `shortseq` package (shortseq/__init__.py:1-
 pack / from_str / from_bytes, ShortSeq64 / ShortSeq192 / ShortSeqVar, ShortSeqCounter,
 read_and_count_fastq, get_domain_* and the MIN/MAX_*_NT constants -- plus the batch entry
 points that are the point of this package: pack_batch, decode_batch, hamming_batch,
-hamming_refset, DeviceCounter and the multi-GPU merge in shortseq_b200.distributed.
+hamming_refset, DeviceCounter, decode_many / hamming_many (str() and ^ over lists of boxed objects with one kernel
+launch per class) and the multi-GPU merge in shortseq_b200.distributed.
 
 All arithmetic runs in hand-written CUDA kernels for sm_100a behind a C ABI
 (include/shortseq_b200.h, libshortseq_b200.so).  There is no CPU fallback.
 """
 from ._lib import CLASS_64, CLASS_192, CLASS_VAR, LibraryError
 from ._runtime import ShortSeqClassError
-from .short_seq import (ShortSeq64, ShortSeq192, ShortSeqVar, pack, from_str, from_bytes, empty,
+from .short_seq import (ShortSeq64, ShortSeq192, ShortSeqVar, pack, from_str, from_bytes, empty, decode_many, hamming_many,
                         get_domain_64, get_domain_192, get_domain_var)
 from .batch import (ReadBatch, ShortSeqArray, pack_batch, pack_mixed, decode_batch, hamming_batch, hamming_refset,
                     synth_reads)
@@ -27,5 +28,5 @@ __all__ = [
     "MIN_64_NT", "MAX_64_NT", "MIN_192_NT", "MAX_192_NT", "MIN_VAR_NT", "MAX_VAR_NT",
     "pack_batch", "pack_mixed", "decode_batch", "hamming_batch", "hamming_refset", "synth_reads",
     "ReadBatch", "ShortSeqArray", "DeviceCounter", "CLASS_64", "CLASS_192", "CLASS_VAR",
-    "LibraryError", "ShortSeqClassError", "empty",
+    "LibraryError", "ShortSeqClassError", "empty", "decode_many", "hamming_many",
 ]

@@ -196,6 +196,61 @@ def _box_many(klass, words, lens):
 empty = _box(CLASS_64, (0,), 0)   # module singleton, like the reference's (short_seq.pyx:7)
 
 
+def _as_arrays(objs):
+    """ShortSeq objects (any mix of classes) -> [(klass, positions, ShortSeqArray)] on the current GPU, one per class."""
+    ctx = _batch.context()
+    groups = {}
+    for i, o in enumerate(objs):
+        groups.setdefault(o._klass, []).append(i)
+    out = []
+    for k, idx in groups.items():
+        sel = [objs[i] for i in idx]
+        lens = np.fromiter((o._length for o in sel), dtype=np.int64, count=len(sel))
+        if k == CLASS_VAR:
+            nb = (lens + 31) // 32
+            wo = np.zeros(len(sel) + 1, dtype=np.int64)
+            np.cumsum(nb, out=wo[1:])
+            flat = np.fromiter((w for o in sel for w in o._packed), dtype=np.uint64, count=int(wo[-1]))
+            arr = _batch.ShortSeqArray(ctx, k, torch.from_numpy(flat.view(np.int64)).to(ctx.device),
+                                       torch.from_numpy(lens.astype(np.int16)).to(ctx.device), torch.from_numpy(wo).to(ctx.device))
+        else:
+            W = 1 if k == CLASS_64 else 3
+            flat = np.fromiter((w for o in sel for w in o._packed), dtype=np.uint64, count=W * len(sel)).view(np.int64)
+            words = torch.from_numpy(flat if W == 1 else flat.reshape(-1, 3)).to(ctx.device)
+            arr = _batch.ShortSeqArray(ctx, k, words, torch.from_numpy(lens.astype(np.uint8)).to(ctx.device))
+        out.append((k, idx, arr))
+    return out
+
+
+def decode_many(seqs):
+    """str() of many ShortSeq objects with one decode kernel per class instead of one launch per object
+    (reference __str__: short_seq_64.pyx:114-121 etc.) -> list of str in the order given."""
+    seqs = list(seqs)
+    out = [""] * len(seqs)
+    for _, idx, arr in _as_arrays([s for s in seqs]):
+        for i, text in zip(idx, arr.decode_to_list()):
+            out[i] = text
+    return out
+
+
+def hamming_many(a, b):
+    """a[i] ^ b[i] for two equal-length lists of ShortSeq objects, one kernel per class -> list of int.
+    Same rules as the reference's __xor__: same class and equal lengths pairwise."""
+    a, b = list(a), list(b)
+    if len(a) != len(b):
+        raise ValueError("hamming_many needs two lists of the same length")
+    out = [0] * len(a)
+    for x, y in zip(a, b):
+        if type(x) is not type(y):
+            raise TypeError(f"Argument 'other' has incorrect type (expected {type(x).__name__}, got {type(y).__name__})")
+    ga, gb = _as_arrays(a), _as_arrays(b)
+    for (_, idx, arr_a), (_, _, arr_b) in zip(ga, gb):
+        d = _batch.hamming_batch(arr_a, arr_b).cpu().numpy()
+        for i, v in zip(idx, d.tolist()):
+            out[i] = int(v)
+    return out
+
+
 def _as_array(obj):
     """A one-element ShortSeqArray on the current GPU holding this object."""
     ctx = _batch.context()

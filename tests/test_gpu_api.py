@@ -4,6 +4,7 @@ Mirrors shortseq/tests/unit_tests_main.py of the reference.
 """
 import random
 
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -127,3 +128,18 @@ def test_counter_from_batch_matches_collections_counter(sq):
     assert len(c) == len(ref)
     assert [str(k).encode() for k in c] == list(ref)            # same first-occurrence order
     assert all(c[sq.pack(k)] == v for k, v in list(ref.items())[:50])
+
+
+def test_decode_many_and_hamming_many(sq):
+    """One kernel per class instead of one launch per object; same answers as str() and ^ on the objects."""
+    rng = np.random.default_rng(321)
+    texts = ["".join(rng.choice(list("ACGT"), size=int(L))) for L in rng.integers(1, 300, size=400)]
+    seqs = [sq.pack(t) for t in texts]
+    assert sq.decode_many(seqs) == texts
+    assert sq.decode_many([]) == []
+    other = [sq.pack("".join(rng.choice(list("ACGT"), size=len(t)))) for t in texts]
+    d = sq.hamming_many(seqs, other)
+    assert d[:40] == [a ^ b for a, b in zip(seqs[:40], other[:40])]
+    assert all(x == sum(c1 != c2 for c1, c2 in zip(t, str_o)) for x, t, str_o in zip(d, texts, sq.decode_many(other)))
+    with pytest.raises(Exception, match="equal length"):
+        sq.hamming_many([sq.pack("ACGT")], [sq.pack("ACG")])
