@@ -19,5 +19,12 @@ for _ in range(3):
     out = arr.decode()
 for _ in range(3):
     d = sq.hamming_batch(arr, arr2)
+refs = sq.pack_batch(sq.synth_reads(256, 256, L, L, seed=5), klass=klass)
+for _ in range(2):
+    sq.hamming_refset(arr, refs, thresh=1)
+ctr = sq.DeviceCounter(klass, expected_unique=n // 10)
+ctr.insert(arr)
+for _ in range(2):
+    ctr.export(8)
 torch.cuda.synchronize()
 print("ok", n, L)
