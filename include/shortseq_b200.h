@@ -122,6 +122,16 @@ int ssq_decode64(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64
                  const int64_t *out_offsets, uint8_t *ascii_out);
 int ssq_decode192(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n,
                   const int64_t *out_offsets, uint8_t *ascii_out);
+/* Fused-offsets form for the fixed classes (no n-entry offsets scan): ssq_decode_tiles sums the lengths of every tile of
+ * SSQ_DECODE_TILE reads and scans the tile totals into tile_base (the buffer holds 2 * ntiles + 2 int64, ntiles =
+ * ceil(n / SSQ_DECODE_TILE); tile_base[ntiles] = total bases, what the caller sizes ascii_out with); ssq_decode64_fused /
+ * ssq_decode192_fused then decode, deriving every read's offset inside the kernel and writing out_offsets[n + 1] as well. */
+#define SSQ_DECODE_TILE 512
+int ssq_decode_tiles(ssq_ctx *ctx, const uint8_t *lens, int64_t n, int max_len /*32 | 96*/, int64_t *tile_base);
+int ssq_decode64_fused(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *tile_base,
+                       int64_t *out_offsets, uint8_t *ascii_out);
+int ssq_decode192_fused(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *tile_base,
+                        int64_t *out_offsets, uint8_t *ascii_out);
 int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, const uint16_t *lens,
                   int64_t n, const int64_t *out_offsets, uint8_t *ascii_out);
 

@@ -49,6 +49,9 @@ PROTOTYPES = {
     "ssq_lens_to_offsets": (_int, [_p, _p, _int, _i64, _p]),
     "ssq_decode64": (_int, [_p, _p, _p, _i64, _p, _p]),
     "ssq_decode192": (_int, [_p, _p, _p, _i64, _p, _p]),
+    "ssq_decode_tiles": (_int, [_p, _p, _i64, _int, _p]),
+    "ssq_decode64_fused": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
+    "ssq_decode192_fused": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "ssq_decodevar": (_int, [_p, _p, _p, _p, _i64, _p, _p]),
     "ssq_hamming_pairs64": (_int, [_p, _p, _p, _p, _p, _i64, _p]),
     "ssq_hamming_pairs192": (_int, [_p, _p, _p, _p, _p, _i64, _p]),

@@ -271,6 +271,17 @@ def decode_batch(arr):
     h = ctx.bind()
     n = len(arr)
     out_off = ctx.empty((n + 1,), torch.int64)
+    if arr.klass in (CLASS_64, CLASS_192) and n > 0:
+        # fused offsets: per-tile totals + a scan over n/512 entries; the decode kernel writes the offsets itself
+        ntiles = (n + 511) // 512
+        tile_base = ctx.empty((2 * ntiles + 2,), torch.int64)
+        _lib.check(L.ssq_decode_tiles(h, ptr(arr.lens), n, 32 if arr.klass == CLASS_64 else 96, ptr(tile_base)))
+        total = int(tile_base[ntiles])
+        out = ctx.empty((max(total, 1),), torch.uint8)
+        fn = L.ssq_decode64_fused if arr.klass == CLASS_64 else L.ssq_decode192_fused
+        _lib.check(fn(h, ptr(arr.words), ptr(arr.lens), n, ptr(tile_base), ptr(out_off), ptr(out)))
+        raise_for_report(ctx.sync())
+        return out[:total], out_off
     _lib.check(L.ssq_lens_to_offsets(h, ptr(arr.lens), 2 if arr.klass == CLASS_VAR else 1, n, ptr(out_off)))
     total = int(out_off[-1]) if n else 0
     out = ctx.empty((max(total, 1),), torch.uint8)

@@ -140,6 +140,124 @@ __global__ void __launch_bounds__(kThreads) decode_fixed_kernel(const u64 *words
     }
 }
 
+// ---- fused offsets: decode without a full offsets scan -------------------------------------------
+// decode_batch used to scan all n lengths into n+1 offsets (4 GB written, then read back by the decode kernel, for
+// 5e8 reads).  Instead: one pass sums the lengths of every 512-read tile, the ~n/512 tile totals are scanned, and the
+// decode kernel derives each read's offset with a block scan of the tile's lengths -- writing out_offsets (a required
+// output) as a by-product.
+__global__ void __launch_bounds__(kThreads) tile_totals_kernel(const uint8_t *lens, int64_t n, int max_len, int64_t *totals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + kDecTile - 1) / kDecTile;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+    const bool aligned = ((uintptr_t)lens & 15) == 0;
+    for (int64_t tile = warp0; tile < ntiles; tile += nwarps) {
+        const int64_t at = tile * kDecTile + lane * 16;
+        u32 sum = 0;
+        if (aligned && at + 16 <= n) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(lens + at);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) sum += min((w[k] >> (8 * b)) & 0xFFu, (u32)max_len);
+        } else {
+            for (int b = 0; b < 16; b++)
+                if (at + b < n) sum += min((u32)lens[at + b], (u32)max_len);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) totals[tile] = (int64_t)sum;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) decode_fixed_fused_kernel(const u64 *words, const uint8_t *lens, int64_t n,
+                                                                      const int64_t *tile_base, int64_t *out_off, uint8_t *out) {
+    constexpr int MAXLEN = 32 * W;
+    constexpr int MAX_CHUNKS = (kDecTile * MAXLEN + 30) / 16 + 1;
+    __shared__ u32 stream[MAX_CHUNKS + 3];
+    __shared__ u32 s_w[kDecRPT][kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t mis = (int64_t)((uintptr_t)out & 15);
+    const int64_t ntiles = (n + kDecTile - 1) / kDecTile;
+    for (int c = threadIdx.x; c < MAX_CHUNKS + 3; c += kThreads) stream[c] = 0;
+    // per-tile state: this thread's reads' lengths and words (the next tile's are loaded a tile ahead)
+    auto load = [&](int64_t tile, int (&len)[kDecRPT], u64 (&w)[kDecRPT][W], int64_t &t0, int64_t &t1) {
+        const int64_t first = tile * kDecTile;
+        t0 = t1 = 0;
+        if (tile < ntiles) { t0 = tile_base[tile]; t1 = tile_base[tile + 1]; }
+#pragma unroll
+        for (int k = 0; k < kDecRPT; k++) {
+            const int64_t i = first + threadIdx.x + k * kThreads;
+            len[k] = -1;
+            if (tile < ntiles && i < n) {
+                len[k] = min((int)lens[i], MAXLEN);
+#pragma unroll
+                for (int j = 0; j < W; j++) w[k][j] = words[(size_t)i * W + j];
+            }
+        }
+    };
+    int clen[kDecRPT]; u64 cw[kDecRPT][W]; int64_t t0, t1;
+    load(blockIdx.x, clen, cw, t0, t1);
+    __syncthreads();
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t first = tile * kDecTile;
+        // offsets of this tile's reads: block scan of their lengths, reads [0, 256) then [256, 512)
+        u32 incl[kDecRPT];
+#pragma unroll
+        for (int k = 0; k < kDecRPT; k++) {
+            u32 v = clen[k] > 0 ? (u32)clen[k] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += x; }
+            incl[k] = v;
+            if (lane == 31) s_w[k][warp] = v;
+        }
+        __syncthreads();
+        int64_t o0[kDecRPT];
+        {
+            u32 run = 0;
+#pragma unroll
+            for (int k = 0; k < kDecRPT; k++) {
+                u32 before = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < kThreads / 32; w++) { const u32 x = s_w[k][w]; if (w < warp) before += x; total += x; }
+                o0[k] = t0 + run + before + incl[k] - (clen[k] > 0 ? (u32)clen[k] : 0u);
+                run += total;
+            }
+        }
+        const int64_t a0 = ((t0 + mis) & ~(int64_t)15) - mis;
+#pragma unroll
+        for (int k = 0; k < kDecRPT; k++) {
+            const int len = clen[k];
+            if (len < 0) continue;
+            const int64_t i = first + threadIdx.x + k * kThreads;
+            out_off[i] = o0[k];
+            if (i == n - 1) out_off[n] = o0[k] + len;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                const int nb = 2 * len - 64 * j;
+                if (nb > 0) {
+                    u64 w = cw[k][j];
+                    if (nb < 64) w &= (1ull << nb) - 1;
+                    deposit64(stream, 2 * (o0[k] - a0) + 64 * j, w);
+                }
+            }
+        }
+        int nlen[kDecRPT]; u64 nw[kDecRPT][W]; int64_t nt0, nt1;
+        load(tile + gridDim.x, nlen, nw, nt0, nt1);                      // in flight during the store phase
+        __syncthreads();
+        store_tile<kThreads>(out, a0, t0, t1, stream, 3);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kDecRPT; k++) {
+            clen[k] = nlen[k];
+#pragma unroll
+            for (int j = 0; j < W; j++) cw[k][j] = nw[k][j];
+        }
+        t0 = nt0; t1 = nt1;
+    }
+}
+
 constexpr int kVarTileReads = 32;
 constexpr int kVarMaxChunks = (kVarTileReads * 1024 + 30) / 16 + 1;
 
@@ -360,6 +478,52 @@ int ssq_decode192(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int6
     DeviceGuard g(ctx->device);
     int grid = grid_for(ctx, (n + kDecTile - 1) / kDecTile, 8);
     decode_fixed_kernel<3><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, out_offsets, ascii_out);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_decode_tiles(ssq_ctx *ctx, const uint8_t *lens, int64_t n, int max_len, int64_t *tile_base) {
+    SSQ_ARG(ctx != nullptr && n >= 0 && tile_base != nullptr, "bad ctx / n / tile_base");
+    SSQ_ARG(max_len == 32 || max_len == 96, "max_len must be 32 (ShortSeq64) or 96 (ShortSeq192)");
+    SSQ_ARG(n == 0 || lens != nullptr, "lens is NULL");
+    DeviceGuard g(ctx->device);
+    const int64_t ntiles = (n + kDecTile - 1) / kDecTile;
+    if (ntiles == 0) { SSQ_CUDA(cudaMemsetAsync(tile_base, 0, sizeof(int64_t), ctx->stream)); return SSQ_OK; }
+    void *scratch = nullptr;     // tile totals live after the scan's own scratch need: take a separate allocation-free slot
+    int64_t *totals = tile_base + ntiles + 1;          // the caller's buffer holds 2 * ntiles + 2 entries: [bases | totals]
+    (void)scratch;
+    tile_totals_kernel<<<grid_for(ctx, (ntiles + kThreads / 32 - 1) / (kThreads / 32), 8), kThreads, 0, ctx->stream>>>(lens, n, max_len, totals);
+    SSQ_LAUNCH_CHECK();
+    return scan_i64(ctx, totals, ntiles, tile_base);
+}
+
+static int check_fused(ssq_ctx *ctx, const void *words, const void *lens, int64_t n, const void *tile_base, const void *out_offsets,
+                       const void *ascii_out) {
+    SSQ_ARG(ctx != nullptr && n >= 0, "bad ctx / n");
+    SSQ_ARG(n == 0 || (words && lens && tile_base && out_offsets && ascii_out), "NULL buffer");
+    return SSQ_OK;
+}
+
+int ssq_decode64_fused(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *tile_base,
+                       int64_t *out_offsets, uint8_t *ascii_out) {
+    int rc = check_fused(ctx, words, lens, n, tile_base, out_offsets, ascii_out);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    if (n == 0) { SSQ_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), ctx->stream)); return SSQ_OK; }
+    int grid = grid_for(ctx, (n + kDecTile - 1) / kDecTile, 8);
+    decode_fixed_fused_kernel<1><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, tile_base, out_offsets, ascii_out);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_decode192_fused(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, int64_t n, const int64_t *tile_base,
+                        int64_t *out_offsets, uint8_t *ascii_out) {
+    int rc = check_fused(ctx, words, lens, n, tile_base, out_offsets, ascii_out);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    if (n == 0) { SSQ_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), ctx->stream)); return SSQ_OK; }
+    int grid = grid_for(ctx, (n + kDecTile - 1) / kDecTile, 8);
+    decode_fixed_fused_kernel<3><<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, lens, n, tile_base, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

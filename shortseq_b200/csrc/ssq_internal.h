@@ -117,6 +117,7 @@ int counter_first_index_indexed(ssq_counter *c, const u64 *words, const uint8_t 
 int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int64_t *out);
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off);
 int scan_u32_counts(ssq_ctx *ctx, const u32 *counts, int64_t n, int64_t *out /*[n+1]*/);
+int scan_i64(ssq_ctx *ctx, const int64_t *values, int64_t n, int64_t *out /*[n+1]*/);
 int scan_synth_lens(ssq_ctx *ctx, uint64_t seed, int64_t first_read, int64_t n, int64_t n_keys,
                     int32_t len_lo, int32_t len_hi, int64_t *offsets);
 

@@ -153,6 +153,10 @@ int scan_lens_to_offsets(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t 
     return scan_exclusive(ctx, LenU16{(const uint16_t *)lens}, n, out);
 }
 
+int scan_i64(ssq_ctx *ctx, const int64_t *values, int64_t n, int64_t *out) {
+    return scan_exclusive(ctx, I64{values}, n, out);
+}
+
 int scan_u32_counts(ssq_ctx *ctx, const u32 *counts, int64_t n, int64_t *out) {
     return scan_exclusive(ctx, CountU32{counts}, n, out);
 }
