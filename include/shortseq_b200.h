@@ -242,6 +242,10 @@ int ssq_host_pack_count(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii,
 int ssq_host_pack_count_lens(ssq_ctx *ctx, ssq_counter *c, const uint8_t *h_ascii, const uint8_t *h_lens,
                              int64_t n, uint64_t *h_words, int64_t chunk_reads, ssq_report *report);
 
+/* Reads per container class of a batch (short_seq.pyx:54-74 picks the class by length): counts is a DEVICE array of 5
+ * int64 -- reads of 0..32, 33..96, 97..1024 and > 1024 nt, then the lowest read index longer than 96 nt (-1 if none). */
+int ssq_classify(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *counts);
+
 /* ---- FASTQ ingest ----------------------------------------------------------
  * Replaces read_and_count_fastq (counter.pyx:57-71) and its getline loop (fast_read.pyx:3-20): h_text is the whole
  * FASTQ file in host memory; every line whose 1-based number is 2 mod 4 is a read, minus its last byte (the newline --

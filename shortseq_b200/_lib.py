@@ -76,6 +76,7 @@ PROTOTYPES = {
     "ssq_ipc_get_handle": (_int, [_p, _p, _p]),
     "ssq_ipc_open": (_int, [_p, _p, C.POINTER(_p)]),
     "ssq_ipc_close": (_int, [_p, _p]),
+    "ssq_classify": (_int, [_p, _p, _i64, _p]),
     "ssq_host_fastq_count": (_int, [_p, _p, _p, _p, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(Report)]),
     "ssq_counter_last_pass_detail": (_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ssq_counter_export": (_int, [_p, _int, _p, _p, _p, _p, _p]),

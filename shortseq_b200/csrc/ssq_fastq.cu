@@ -163,6 +163,21 @@ struct Carve {
 
 }  // namespace
 
+// Reads per container class of a batch given as offsets (ssq_classify; short_seq.pyx:54-74 decides the class
+// from the length).  counts (device, 5 entries): reads of 0..32, 33..96, 97..1024 and > 1024 nt, then the lowest read
+// index longer than 96 nt (-1 if none).
+extern "C" int ssq_classify(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *counts) {
+    SSQ_ARG(ctx != nullptr && counts != nullptr && n >= 0, "bad arguments");
+    SSQ_ARG(n == 0 || offsets != nullptr, "offsets is NULL");
+    DeviceGuard g(ctx->device);
+    SSQ_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), ctx->stream));
+    SSQ_CUDA(cudaMemsetAsync(counts + 4, 0xFF, sizeof(int64_t), ctx->stream));
+    if (n == 0) return SSQ_OK;
+    class_count_kernel<<<grid_for(ctx, (n + kFqThreads - 1) / kFqThreads, 8), kFqThreads, 0, ctx->stream>>>(offsets, offsets + 1, n, (u64 *)counts);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
 extern "C" int ssq_host_fastq_count(ssq_ctx *ctx, ssq_counter *c64, ssq_counter *c192, const uint8_t *h_text, int64_t nbytes,
                                     int64_t chunk_bytes, int track_first_index, int64_t *n_reads, int64_t *n_longer,
                                     int64_t *first_longer, ssq_report *report) {

@@ -143,3 +143,22 @@ def test_decode_many_and_hamming_many(sq):
     assert all(x == sum(c1 != c2 for c1, c2 in zip(t, str_o)) for x, t, str_o in zip(d, texts, sq.decode_many(other)))
     with pytest.raises(Exception, match="equal length"):
         sq.hamming_many([sq.pack("ACGT")], [sq.pack("ACG")])
+
+
+def test_classify(sq):
+    """ssq_classify: reads per container class from the offsets (reference short_seq.pyx:54-74)."""
+    import torch
+    from shortseq_b200 import _lib
+    from shortseq_b200._runtime import context, ptr
+    rng = np.random.default_rng(11)
+    lens = rng.choice([0, 1, 31, 32, 33, 96, 97, 500, 1024, 1025, 4000], size=50_000)
+    off = np.zeros(lens.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    ctx = context()
+    d_off = torch.from_numpy(off).to(ctx.device)
+    out = torch.empty(5, dtype=torch.int64, device=ctx.device)
+    _lib.check(_lib.lib().ssq_classify(ctx.bind(), ptr(d_off), int(lens.size), ptr(out)))
+    got = out.cpu().numpy()
+    exp = [(lens <= 32).sum(), ((lens > 32) & (lens <= 96)).sum(), ((lens > 96) & (lens <= 1024)).sum(), (lens > 1024).sum(),
+           int(np.nonzero(lens > 96)[0][0])]
+    assert got.tolist() == [int(x) for x in exp]
