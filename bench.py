@@ -267,7 +267,7 @@ def run_ours(args):
     import shortseq_b200 as sq
     from shortseq_b200 import _lib
     from shortseq_b200._runtime import ptr
-    from shortseq_b200.distributed import PeerExchange, merge_alltoall, merge_peer
+    from shortseq_b200.distributed import PeerExchange, PeerExchangeUnavailable, merge_alltoall, merge_peer
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -291,6 +291,7 @@ def run_ours(args):
         owner = sq.DeviceCounter(klass, expected_unique=int(1.1 * u / world) + 1024, hash_rot=world.bit_length() - 1)
         if klass == sq.CLASS_64 and not args.nccl_exchange:
             exchange = PeerExchange(ctx)
+    state = {"exchange": exchange}
     h = ctx.bind()
     kernel_ms, uniques_seen, phase_ms = [], [0], []
 
@@ -305,8 +306,15 @@ def run_ours(args):
         phase_ms.append(tuple(x.value for x in d))
         if world > 1:
             _lib.check(lib.ssq_counter_clear(owner.handle))
-            if exchange is not None:
-                merge_peer(local, owner, exchange)        # export kernel stores straight into the owners' memory (NVLink)
+            if state["exchange"] is not None:
+                try:
+                    merge_peer(local, owner, state["exchange"])   # export kernel stores straight into the owners' memory (NVLink)
+                except PeerExchangeUnavailable as e:              # raised on every rank alike: switch to NCCL for good
+                    if rank == 0:
+                        print(f"bench: {e}; using the NCCL all-to-all exchange", file=sys.stderr, flush=True)
+                    state["exchange"] = None
+                    _lib.check(lib.ssq_counter_clear(owner.handle))
+                    merge_alltoall(local, owner=owner)
             else:
                 merge_alltoall(local, owner=owner)        # export, then NCCL all-to-all
             uniques_seen[0] = len(owner)
@@ -413,8 +421,8 @@ def run_ours(args):
             assert rep.code == 0
             if world > 1:
                 _lib.check(lib.ssq_counter_clear(eowner.handle))
-                if exchange is not None:
-                    merge_peer(ectr, eowner, exchange)
+                if state["exchange"] is not None:
+                    merge_peer(ectr, eowner, state["exchange"])
                 else:
                     merge_alltoall(ectr, owner=eowner)
                 return len(eowner)
@@ -450,8 +458,8 @@ def run_ours(args):
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
-        if exchange is not None:
-            exchange.close()
+        if state["exchange"] is not None:
+            state["exchange"].close()
         dist.destroy_process_group()
 
 

@@ -83,6 +83,11 @@ def merge_alltoall(local, group=None, owner=None):
     return owner
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank cannot share or map the peer buffers (CUDA IPC); callers fall back to
+    merge_alltoall (NCCL)."""
+
+
 class PeerExchange:
     """Receive buffers of this rank for the multi-GPU merge, mapped into every other rank of the box through CUDA
     IPC, so that ssq_counter_export_to on the sending GPU stores the tuples an owner is due straight into the
@@ -131,26 +136,40 @@ class PeerExchange:
         cap = int(need * 1.25) + 1024
         rb_cap = max(int(need_regions), 1)
         handles = torch.zeros(4 * 64, dtype=torch.uint8)
-        for k, nbytes in enumerate((8 * cap, cap, 8 * cap, 8 * self.world * (rb_cap + 1))):
-            p = C.c_void_p()
-            _lib.check(lib.ssq_malloc(h, nbytes, C.byref(p)))
-            self.mine[k] = p.value
-            hb = (C.c_ubyte * 64)()
-            _lib.check(lib.ssq_ipc_get_handle(h, p, hb))
-            handles[64 * k: 64 * (k + 1)] = torch.frombuffer(bytes(hb), dtype=torch.uint8)
+        failure = None
+        try:
+            for k, nbytes in enumerate((8 * cap, cap, 8 * cap, 8 * self.world * (rb_cap + 1))):
+                p = C.c_void_p()
+                _lib.check(lib.ssq_malloc(h, nbytes, C.byref(p)))
+                self.mine[k] = p.value
+                hb = (C.c_ubyte * 64)()
+                _lib.check(lib.ssq_ipc_get_handle(h, p, hb))
+                handles[64 * k: 64 * (k + 1)] = torch.frombuffer(bytes(hb), dtype=torch.uint8)
+        except Exception as e:  # noqa: BLE001 -- the ranks agree on the outcome below
+            failure = e
         mine = handles.to(self.ctx.device)
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine, group=self.group)
-        for r in range(self.world):
-            hr = gathered[r].cpu().numpy().tobytes()
-            for k in range(4):
-                if r == self.rank:
-                    self.peer[k][r] = self.mine[k]
-                else:
-                    p = C.c_void_p()
-                    _lib.check(lib.ssq_ipc_open(h, hr[64 * k: 64 * (k + 1)], C.byref(p)))
-                    self.peer[k][r] = p.value
-                    self._opened.append(p.value)
+        if failure is None:
+            try:
+                for r in range(self.world):
+                    hr = gathered[r].cpu().numpy().tobytes()
+                    for k in range(4):
+                        if r == self.rank:
+                            self.peer[k][r] = self.mine[k]
+                        else:
+                            p = C.c_void_p()
+                            _lib.check(lib.ssq_ipc_open(h, hr[64 * k: 64 * (k + 1)], C.byref(p)))
+                            self.peer[k][r] = p.value
+                            self._opened.append(p.value)
+            except Exception as e:  # noqa: BLE001
+                failure = e
+        # every rank must take the same road: if CUDA IPC is not available to one of them, none uses it
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int64, device=self.ctx.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self._release()
+            raise PeerExchangeUnavailable(f"CUDA IPC peer buffers could not be set up on every rank ({failure})")
         self.cap = cap
         self.rb_cap = rb_cap
 
