@@ -545,6 +545,170 @@ count_regions_kernel(TableView t, RegionParts rp) {
     }
 }
 
+// Level 3, second version: the same CTA-per-region layout, but without the per-iteration queue bookkeeping of
+// count_regions_kernel.  Every lane holds KPT keys in registers and all lanes make up to ROUNDS probes of each key
+// under predication -- independent shared-memory loads in flight, no warp-level vote per probe.  The few keys still
+// unresolved after ROUNDS probes (a few percent at the loads the table policy allows) are parked in a CTA-wide queue
+// in shared memory and finished by a plain per-thread probe loop once the stream is exhausted (or when the queue fills).
+constexpr int kCount2KPT = 4;
+constexpr int kCount2Rounds = 3;
+constexpr int kCount2Chunk = 32 * kCount2KPT;
+constexpr int kCount2Queue = 1024;          // parked keys per CTA
+
+template <int THREADS>
+static size_t count_regions2_smem(int log2_region, unsigned nseg) {
+    return ((size_t)12 << log2_region) + sizeof(u64) * kCount2Queue + sizeof(u32) * (2 * nseg + 2);
+}
+
+// one complete probe sequence of `key` starting at its home slot (shared-memory table at ks_a / ds_a)
+__device__ __forceinline__ void probe_to_the_end(u32 ks_a, u32 ds_a, u32 rmask, u32 hi_shift, u64 key, u32 &my_new, u32 &overflow) {
+    const u32 home = ((u32)(key >> 32) >> hi_shift) & rmask;
+    u32 off = home;
+    for (;;) {
+        u64 cur = lds_u64(ks_a + off * 8);
+        if (cur == 0) {
+            cur = atoms_cas_u64(ks_a + off * 8, 0ull, key);
+            if (cur == 0) { ++my_new; cur = key; }
+        }
+        if (cur == key) { reds_add_u32(ds_a + off * 4, 1u); return; }
+        off = (off + 1) & rmask;
+        if (off == home) { ++overflow; return; }
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3)
+count_regions2_kernel(TableView t, RegionParts rp) {
+    extern __shared__ __align__(16) u64 dyn_region[];
+    __shared__ u32 s_new[THREADS / 32];
+    __shared__ u32 s_qn;
+    constexpr u32 W = THREADS / 32;
+    const u32 R = 1u << t.log2_region, rmask = R - 1;
+    u64 *ks = dyn_region;
+    u32 *ds = reinterpret_cast<u32 *>(dyn_region + R);
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 *pq = dyn_region + R + R / 2;                                             // parked keys
+    u32 *pre = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + kCount2Queue);   // [nseg + 1] exclusive scan of the segment sizes
+    u32 *segoff = pre + (rp.slices << (8 - rp.qbits)) + 1;                        // [nseg] first entry of stream segment k in rp.keys
+    const u32 region = blockIdx.x;
+    const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
+    const u32 p = region >> rp.qbits, q = region & ((1u << rp.qbits) - 1);
+    const u32 nseg = rp.slices << sub_bits;
+    auto seg_index = [&](u32 k) -> size_t { return ((size_t)p * rp.slices + (k >> sub_bits)) * kParts + ((q << sub_bits) | (k & sub_mask)); };
+    if (warp == 0) {                                          // pre[] = exclusive scan of the segment sizes
+        u32 carry = 0;
+        for (u32 b = 0; b < nseg; b += 32) {
+            const u32 k = b + lane;
+            const u32 v = k < nseg ? rp.seg_count[seg_index(k)] : 0u;
+            u32 incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+            if (k < nseg) {
+                pre[k + 1] = carry + incl;
+                segoff[k] = (u32)(seg_index(k) * rp.seg_cap);
+            }
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) { pre[0] = 0; s_qn = 0; }
+    }
+    const u64 keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
+    ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
+    const bool was_empty = t.region_count[region] == 0;
+    for (u32 i = threadIdx.x; i < R; i += THREADS) {
+        ks[i] = was_empty ? 0ull : ld_hint_v2u64(gslots + i, keep).x;
+        ds[i] = 0;
+    }
+    __syncthreads();
+    const u32 total = pre[nseg];
+    const u32 hi_shift = (u32)(64 - t.log2_cap) - 32;   // the home slot's region offset lies in the key's high word
+    const u32 ks_a = smem_addr(ks), ds_a = smem_addr(ds), pq_a = smem_addr(pq);
+    u32 my_new = 0, overflow = 0, seg = 0;
+    u64 nk[kCount2KPT];
+    auto load_chunk = [&](u32 c) {
+        const u32 i0 = c * kCount2Chunk;
+        while (i0 >= pre[seg + 1]) ++seg;                       // warp-uniform: the segment the chunk starts in
+        if (i0 + kCount2Chunk <= pre[seg + 1]) {                // the usual case: the whole chunk lies in one segment
+            const u64 *src = rp.keys + (segoff[seg] + (i0 - pre[seg])) + lane;
+#pragma unroll
+            for (int r = 0; r < kCount2KPT; r++) nk[r] = ld_stream_u64(src + r * 32, drop);
+        } else {                                                // it straddles segments or the end of the stream
+            u32 sg = seg;
+#pragma unroll
+            for (int r = 0; r < kCount2KPT; r++) {
+                const u32 i = i0 + r * 32 + lane;
+                nk[r] = 0;
+                if (i < total) {
+                    while (i >= pre[sg + 1]) ++sg;
+                    nk[r] = ld_stream_u64(rp.keys + (segoff[sg] + (i - pre[sg])), drop);
+                }
+            }
+        }
+    };
+    u32 c = warp;
+    if (c * kCount2Chunk < total) load_chunk(c);
+    while (c * kCount2Chunk < total) {
+        u64 key[kCount2KPT];
+        u32 off[kCount2KPT];
+#pragma unroll
+        for (int j = 0; j < kCount2KPT; j++) {
+            key[j] = nk[j];
+            off[j] = ((u32)(key[j] >> 32) >> hi_shift) & rmask;
+        }
+        c += W;
+        if (c * kCount2Chunk < total) load_chunk(c);          // in flight during the probes
+#pragma unroll
+        for (int r = 0; r < kCount2Rounds; r++) {
+            u64 cur[kCount2KPT];
+#pragma unroll
+            for (int j = 0; j < kCount2KPT; j++) cur[j] = key[j] != 0 ? lds_u64(ks_a + off[j] * 8) : 1ull;
+#pragma unroll
+            for (int j = 0; j < kCount2KPT; j++) {
+                if (key[j] != 0) {
+                    if (cur[j] == 0) {                       // empty slot: claim it
+                        cur[j] = atoms_cas_u64(ks_a + off[j] * 8, 0ull, key[j]);
+                        if (cur[j] == 0) { ++my_new; cur[j] = key[j]; }
+                    }
+                    if (cur[j] == key[j]) { reds_add_u32(ds_a + off[j] * 4, 1u); key[j] = 0; }
+                    else off[j] = (off[j] + 1) & rmask;
+                }
+            }
+        }
+        // park what is left (a key restarts from its home slot later: the probes it repeats all hit occupied slots)
+#pragma unroll
+        for (int j = 0; j < kCount2KPT; j++) {
+            if (key[j] != 0) {
+                const u32 pos = atomicAdd(&s_qn, 1u);
+                if (pos < (u32)kCount2Queue) sts_u64(pq_a + pos * 8, key[j]);
+                else probe_to_the_end(ks_a, ds_a, rmask, hi_shift, key[j], my_new, overflow);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const u32 nq = min(s_qn, (u32)kCount2Queue);
+        for (u32 i = threadIdx.x; i < nq; i += THREADS) probe_to_the_end(ks_a, ds_a, rmask, hi_shift, lds_u64(pq_a + i * 8), my_new, overflow);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < R; i += THREADS) {
+        const u32 d = ds[i];
+        if (was_empty) gslots[i] = make_ulonglong2(ks[i], (u64)d);
+        else if (d) gslots[i] = make_ulonglong2(ks[i], gslots[i].y + d);
+    }
+    if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+    if (lane == 0) s_new[warp] = my_new;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (u32 k = 0; k < W; k++) tot += s_new[k];
+        if (tot) {
+            atomicAdd(t.size, (u64)tot);
+            red_add_u32(t.region_count + region, tot);
+        }
+    }
+}
+
 // Fallback for tables whose regions exceed shared memory: insert the level-1 partitions in order.  Block b handles
 // the segment that scatter CTA (b % num_ctas) filled for partition (b / num_ctas); blocks are scheduled in index
 // order, so at any time the whole GPU works on one or two neighbouring partitions whose table range (cap/256
@@ -1134,7 +1298,24 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
     const unsigned nseg = rp.slices << (8 - rp.qbits);
     const int cthreads = env_int("SSQ_COUNT_THREADS", 384, 256, 512);
-    if (cthreads == 256) {
+    if (env_int("SSQ_COUNT_V2", 1, 0, 1)) {
+        if (cthreads == 256) {
+            const size_t bytes = count_regions2_smem<256>(t.log2_region, nseg);
+            rc = set_max_smem((const void *)count_regions2_kernel<256>, bytes);
+            if (rc) return rc;
+            count_regions2_kernel<256><<<nregions, 256, bytes, ctx->stream>>>(t, rp);
+        } else if (cthreads == 512) {
+            const size_t bytes = count_regions2_smem<512>(t.log2_region, nseg);
+            rc = set_max_smem((const void *)count_regions2_kernel<512>, bytes);
+            if (rc) return rc;
+            count_regions2_kernel<512><<<nregions, 512, bytes, ctx->stream>>>(t, rp);
+        } else {
+            const size_t bytes = count_regions2_smem<384>(t.log2_region, nseg);
+            rc = set_max_smem((const void *)count_regions2_kernel<384>, bytes);
+            if (rc) return rc;
+            count_regions2_kernel<384><<<nregions, 384, bytes, ctx->stream>>>(t, rp);
+        }
+    } else if (cthreads == 256) {
         const size_t bytes = count_regions_smem<256>(t.log2_region, nseg);
         rc = set_max_smem((const void *)count_regions_kernel<256>, bytes);
         if (rc) return rc;

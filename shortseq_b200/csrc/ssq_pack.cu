@@ -176,6 +176,15 @@ __device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets,
     return o;
 }
 
+// This thread's part of the test "the tile is kTileReads reads of exactly 32 bytes, the first one on a 16-byte address
+// boundary, every 16-byte chunk prefetched" (fast path of pack_fixed_kernel; all threads must agree).
+__device__ __forceinline__ bool tile_is_uniform32(const TileOffsets &o, const TileGeom &g, bool prefetched) {
+    bool u = prefetched && o.nreads == kTileReads && g.lead == 0 && (o.t1 - o.t0) == (int64_t)kTileReads * 32;
+#pragma unroll
+    for (int k = 0; k < kRPT; k++) u = u && o.start[k] == o.t0 + 32 * (int64_t)(threadIdx.x + k * kPackThreads);
+    return u;
+}
+
 // ---- ShortSeq64 / ShortSeq192 ------------------------------------------------------------------
 // Persistent CTAs walk the tiles with a grid stride.  The loop is software-pipelined: while a tile is being
 // extracted, the 16-byte loads of the CTA's next tile and the offsets of the one after are already in flight.
@@ -201,6 +210,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
     __shared__ u32 s_unstaged_new, s_ovf_n;
+    __shared__ u32 s_uni[3];                            // fast-path votes, see the tile loop
     const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap * RW : nullptr;
 
@@ -225,6 +235,18 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     bool prefetched = cur_ok && geom.interior;
     if (prefetched) issue_tile_loads<kPackThreads>(geom, v);
     TileOffsets nxt = load_tile_offsets(a.offsets, a.n, tile + stride);
+    // FAST PATH (ShortSeq64): a full tile of 32-nt reads whose first byte sits on a 16-byte address boundary.  Chunk c
+    // of the tile is then half (c & 1) of read c >> 1, so the prefetched 16-byte chunks are encoded in registers and a
+    // read's two halves meet through one shuffle between neighbouring lanes: no code stream in shared memory, no
+    // per-read offsets, no extraction.  Whether a tile qualifies is voted one tile ahead (its offsets are already in
+    // registers) at the barrier every tile has anyway.
+    const bool lens_aligned = ((uintptr_t)a.lens & 15) == 0;
+    bool cur_fast = false;
+    u32 vote_slot = 0;
+    if constexpr (KLASS == SSQ_CLASS_64) {
+        if (threadIdx.x == 0) s_uni[0] = 1;
+        cur_fast = __syncthreads_and(tile_is_uniform32(cur, geom, prefetched)) != 0 && lens_aligned;
+    }
 
     for (; tile < ntiles; tile += stride) {
         const int64_t first = tile * kTileReads;
@@ -233,7 +255,11 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
         const int tile_bytes = cur_ok ? (int)(cur.t1 - cur.t0) : 0;
         const int lead = geom.lead;
         u32 bad = 0;
-        if (cur_ok) {
+        u32 fc[kLoadUnroll];                                      // fast path: codes of this thread's four chunks
+        if (cur_fast) {
+#pragma unroll
+            for (int j = 0; j < kLoadUnroll; j++) fc[j] = encode16(v[j], bad);
+        } else if (cur_ok) {
 #pragma unroll
             for (int k = 0; k < kRPT; k++) {
                 const int r = threadIdx.x + k * kPackThreads;
@@ -265,9 +291,64 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
         if (nprefetched) issue_tile_loads<kPackThreads>(ngeom, v);
         const TileOffsets nxt2 = load_tile_offsets(a.offsets, a.n, tile + 2 * stride);
 
+        // The barrier's own vote carries "some byte was invalid"; the vote on the next tile's uniformity rides along in one
+        // of three rotating shared flags: a warp that disagrees clears the flag before the barrier, thread 0 re-arms the
+        // flag of the next iteration (last read two barriers ago, next cleared only after this barrier).
+        bool nxt_fast = false;
+        if constexpr (KLASS == SSQ_CLASS_64) {
+            if (threadIdx.x == 0) s_uni[(vote_slot + 1) % 3] = 1;
+            if (!__all_sync(0xFFFFFFFFu, tile_is_uniform32(nxt, ngeom, nprefetched)) && (threadIdx.x & 31) == 0) s_uni[vote_slot] = 0;
+        }
         const int tile_bad = __syncthreads_or(bad != 0);
+        if constexpr (KLASS == SSQ_CLASS_64) {
+            nxt_fast = s_uni[vote_slot] != 0 && lens_aligned;
+            vote_slot = (vote_slot + 1) % 3;
+        }
 
-        if (cur_ok) {
+        bool flushed = false;
+        if (cur_fast) {
+            if constexpr (KLASS == SSQ_CLASS_64) {
+                // lanes 2m / 2m+1 hold the low / high half of read (t >> 1) + 128 j in fc[j]; the even lane assembles the
+                // reads of j = 0, 1, the odd lane those of j = 2, 3
+                const bool odd = threadIdx.x & 1;
+                const u32 x0 = __shfl_xor_sync(0xFFFFFFFFu, odd ? fc[0] : fc[2], 1);
+                const u32 x1 = __shfl_xor_sync(0xFFFFFFFFu, odd ? fc[1] : fc[3], 1);
+                u64 w2[2];
+                w2[0] = odd ? ((u64)fc[2] << 32) | x0 : ((u64)x0 << 32) | fc[0];
+                w2[1] = odd ? ((u64)fc[3] << 32) | x1 : ((u64)x1 << 32) | fc[1];
+                const int r0 = (int)(threadIdx.x >> 1) + (odd ? 2 * (kPackThreads / 2) : 0);   // reads r0 and r0 + 128
+                bool ok2[2] = {true, true};
+                if (__any_sync(0xFFFFFFFFu, bad != 0)) {              // some byte of this warp's chunks is invalid: exact re-check
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int r = r0 + q * (kPackThreads / 2);
+                        if (read_has_bad_base(a.ascii + t0 + 32 * r, 32)) {
+                            ok2[q] = false;
+                            atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + first + r));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; q++) a.words[(size_t)first + r0 + q * (kPackThreads / 2)] = w2[q];
+                if (threadIdx.x < kTileReads / 16)
+                    reinterpret_cast<uint4 *>((uint8_t *)a.lens + first)[threadIdx.x] = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    if (MODE == kModeDirect && ok2[q]) {
+                        bool is_new = false;
+                        insert64(t, w2[q], 32u, 1ull, is_new);
+                        my_new += is_new ? 1u : 0u;
+                    }
+                    if constexpr (MODE == kModeScatter) {
+                        if (ok2[q]) {
+                            const u64 h2 = rotl64(mix64(w2[q]), t.rot);
+                            const u64 key = key64_of(h2, 32u);
+                            if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
+                        }
+                    }
+                }
+            }
+        } else if (cur_ok) {
 #pragma unroll
             for (int k = 0; k < kRPT; k++) {
                 const int r = threadIdx.x + k * kPackThreads;
@@ -324,21 +405,25 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                     }
                 }
             }
-            if constexpr (MODE == kModeScatter) {
-                // every flush_every-th tile: move the complete 128-byte lines of the staging rings to global memory
-                if (++since_flush >= pv.flush_every) {
-                    since_flush = 0;
-                    __syncthreads();
-                    flush_lines<false, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
-                }
+        }
+        if constexpr (MODE == kModeScatter) {
+            // every flush_every-th tile: move the complete 128-byte lines of the staging rings to global memory
+            if ((cur_fast || cur_ok) && ++since_flush >= pv.flush_every) {
+                since_flush = 0;
+                flushed = true;
+                __syncthreads();
+                flush_lines<false, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
             }
         }
-        __syncthreads();   // codes[] / srel[] are rewritten by the next tile
+        // codes[] / srel[] are rewritten by the next tile, and the rings are staged into again after a flush; a fast-path
+        // tile touched neither codes[] nor srel[]
+        if (!cur_fast || flushed) __syncthreads();
 
-        cur = nxt; cur_ok = nxt_ok; geom = ngeom; prefetched = nprefetched; nxt = nxt2;
+        cur = nxt; cur_ok = nxt_ok; geom = ngeom; prefetched = nprefetched; nxt = nxt2; cur_fast = nxt_fast;
     }
     if constexpr (MODE == kModeScatter) {
-        flush_lines<true, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);   // the loop ended with a barrier
+        __syncthreads();   // a fast-path tile ends without a barrier
+        flush_lines<true, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
         __syncthreads();
         for (int p = threadIdx.x; p < kParts; p += kPackThreads)
             pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);

@@ -104,11 +104,15 @@ class PeerExchange:
         self._opened = []
 
     def _release(self):
+        """Collective.  CUDA requires every importer to close its mapping (cudaIpcCloseMemHandle) BEFORE the exporter
+        frees the memory, so: (1) unmap the peers' buffers, (2) barrier, (3) free this rank's own."""
         from . import _lib
         lib, h = _lib.lib(), self.ctx.bind()
         for p in self._opened:
             lib.ssq_ipc_close(h, p)
         self._opened = []
+        self.peer = [[0] * self.world for _ in range(4)]
+        dist.barrier(self.group)                   # nobody still maps what is freed next
         for p in self.mine:
             if p:
                 lib.ssq_free(h, p)
@@ -117,9 +121,9 @@ class PeerExchange:
         self.rb_cap = 0
 
     def close(self):
-        """Collective: unmap the peers' buffers, then free this rank's."""
+        """Collective: unmap the peers' buffers, barrier, then free this rank's."""
         torch.cuda.synchronize(self.ctx.device)
-        dist.barrier(self.group)
+        dist.barrier(self.group)                   # nobody is still writing into, or reading from, the buffers
         self._release()
 
     def ensure(self, need, need_regions=0):

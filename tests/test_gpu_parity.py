@@ -392,6 +392,44 @@ def test_counter_region_path_table_sizes(sq, oracle, log2_slots):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
 
 
+@pytest.mark.parametrize("log2_slots", [28, 29])
+def test_counter_bench_geometry(sq, oracle, log2_slots):
+    """The geometry bench.py's headline runs on: DeviceCounter(expected_unique = 1e8) -> 2^28 slots =
+    65536 regions of 4096 slots, one level-2 partition per region, 6 slices; n >= cap/4 reads so that the deferred path is
+    taken; two passes (empty, then populated table) against the C oracle's counts of the same reads.  2^29 slots: the
+    8192-slot regions of the next table size."""
+    import torch
+    from tests.util import canon_counts
+    free, _ = torch.cuda.mem_get_info()
+    if free < (30 << 30) * (log2_slots - 27):
+        pytest.skip("not enough device memory")
+    cap = 1 << log2_slots
+    n = cap // 4 + 1_000_003                    # >= cap / 4: use_deferred() holds
+    u = n // 3                                  # ~ 2.3e7 distinct 32-nt sequences (every key id is its own sequence)
+    b = sq.synth_reads(n, u, 32, 32, seed=0x5EED0001)
+    buf, off = b.ascii.cpu().numpy(), b.offsets.cpu().numpy()
+    ow, ol, _ = oracle.pack_batch(0, buf, off)
+    uw, ul, uc, _ = oracle.count(ow, ol, 1)
+    ew, el, ec = canon_counts(uw, ul, uc)
+    del buf, off, uw, ul, uc
+    ctr = sq.DeviceCounter(0, expected_unique=cap // 2 - cap // 8)     # 1.0e8 for 2^28 slots
+    assert ctr.capacity() == cap
+    arr = ctr.pack_count(b)
+    w, l, _ = arr.to_host()
+    assert np.array_equal(w, ow) and np.array_equal(l, ol)
+    del w, l
+    for npass in (1, 2):
+        if npass == 2:
+            ctr.pack_count(b)                   # second pass: every region is loaded, counted into and written back
+        assert len(ctr) == len(ec)
+        keys, counts, _, _ = ctr.export(1)
+        kw, kl, _ = keys.to_host()
+        gw, gl, gc = canon_counts(kw, kl, counts.cpu().numpy())
+        assert np.array_equal(gw, ew) and np.array_equal(gl, el), "exported keys differ from the oracle"
+        assert np.array_equal(gc, npass * ec), "multiplicities differ from the oracle"
+        del keys, counts, kw, kl, gw, gl, gc
+
+
 @pytest.mark.parametrize("skew", [False, True])
 def test_counter_deferred_192(sq, oracle, skew):
     """ShortSeq192 tables too large for L2: records {w0, w1, w2, meta} are scattered to 256 hash partitions by the pack
