@@ -159,7 +159,13 @@ int ssq_hamming_refset(ssq_ctx *ctx, int words_per_seq, const uint64_t *q, const
  * __eq__ (short_seq_64.pyx:41-44, short_seq_192.pyx:35-41); value = multiplicity.  The
  * reference's dict slot hash (word0, util.pxd:68-70) is not observable; the table mixes
  * its own.  klass is SSQ_CLASS_64 or SSQ_CLASS_192 (the reference never deduplicates
- * ShortSeqVar, SURVEY trap T3).  expected_unique sizes the table (it grows if exceeded);
+ * ShortSeqVar, SURVEY trap T3).  expected_unique > 0 is the caller's bound on the distinct keys:
+ * the table gets at least twice that many slots and every batch is counted in one pass; the table
+ * grows before a pass that could load it beyond 75 % and after one that left it above 60 %, and a
+ * table that holds more keys than the bound continues as if expected_unique were 0.  Only a single
+ * pass that alone brings far more distinct keys than the bound can fill a table region; that is
+ * reported as SSQ_ERR_TABLE_FULL by ssq_ctx_sync (the counter must then be discarded).
+ * expected_unique = 0: no bound -- gated sub-batches, the table grows x4 whenever it has to.
  * hash_rot (0..56) rotates the slot hash so that a table holding only the keys of one
  * hash partition (multi-GPU owner tables) still spreads over all slots. */
 int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int hash_rot,

@@ -20,7 +20,11 @@ class DeviceCounter:
     """A GPU hash table of (length, packed words) -> count for one container class.
 
     klass: CLASS_64 or CLASS_192 (the reference never deduplicates ShortSeqVar keys,
-    SURVEY trap T3).  expected_unique sizes the table; it grows when exceeded.
+    SURVEY trap T3).  expected_unique (a bound on the distinct keys; 0 = unknown) sizes the table to at least twice
+    the bound and lets a batch be counted in one pass.  The table grows before a pass that could load it beyond 75 %
+    and after a pass that left it more than 60 % full; once it holds more keys than the bound it continues in the
+    conservative mode of expected_unique = 0 (gated sub-batches, grows as needed).  Only one single pass that brings
+    far more distinct keys than the bound can still overflow (LibraryError "counter table overflow").
     """
 
     def __init__(self, klass, expected_unique=0, hash_rot=0, device=None):
@@ -188,7 +192,7 @@ def count_reads(reads, device=None):
     for k, idx, sub_ascii, sub_off in _batch.split_by_class(h_ascii, h_off):
         if k == CLASS_VAR:
             continue
-        ctr = DeviceCounter(k, expected_unique=min(idx.size, 1 << 26), device=device)
+        ctr = DeviceCounter(k, expected_unique=idx.size, device=device)
         b = _batch.ReadBatch.make(sub_ascii, sub_off, ctr.ctx.device)
         arr = ctr.pack_count(b, check=False)
         rep = ctr.ctx.sync()
@@ -256,7 +260,7 @@ class ShortSeqCounter(dict):
         b = _batch.ReadBatch.make(source, offsets, device)
         if klass is None:
             klass = CLASS_64 if b.n == 0 else _batch.class_of_length(int(b.lengths_host()[0]))
-        ctr = DeviceCounter(klass, expected_unique=min(b.n, 1 << 26), device=b.ctx.device)
+        ctr = DeviceCounter(klass, expected_unique=b.n, device=b.ctx.device)
         arr = ctr.pack_count(b)
         ctr.track_first_index(arr)
         keys, counts, first, _ = ctr.export(1, with_first_index=True)

@@ -15,8 +15,11 @@
 //     appends each key to one of 256 hash partitions; phase 2 (count_parts_kernel) walks the
 //     partitions in order, so all SMs insert into the same 1/256 of the table at a time and that
 //     region stays resident in L2 -- random DRAM sector traffic becomes two streaming passes over
-//     8 bytes per read.  After the pass the table grows (x2) once it is more than 60 % full; a bound
-//     exceeded so badly that probing fails is reported as SSQ_ERR_TABLE_FULL, never silently.
+//     8 bytes per read.  Before a pass the table grows if size + min(n, bound - size) keys would load it beyond 75 %
+//     (make_room); after the pass it grows (x2) once it is more than 60 % full; a table that holds more keys than the
+//     bound has proven the bound wrong and the counter continues in the conservative mode.  Only a single pass that
+//     alone brings far more distinct keys than the bound can still fill a region: that is reported as
+//     SSQ_ERR_TABLE_FULL, never silently.
 #include <stdlib.h>
 #include "ssq_internal.h"
 #include "ssq_table.cuh"
@@ -545,35 +548,35 @@ count_regions_kernel(TableView t, RegionParts rp) {
     }
 }
 
-// Level 3, second version: the same CTA-per-region layout, but without the per-iteration queue bookkeeping of
-// count_regions_kernel.  Every lane holds KPT keys in registers and all lanes make up to ROUNDS probes of each key
-// under predication -- independent shared-memory loads in flight, no warp-level vote per probe.  The few keys still
-// unresolved after ROUNDS probes (a few percent at the loads the table policy allows) are parked in a CTA-wide queue
-// in shared memory and finished by a plain per-thread probe loop once the stream is exhausted (or when the queue fills).
+// Level 3, second version: the same CTA-per-region layout, but the queue of count_regions_kernel only sees the keys
+// that need it.  A warp streams its share of the region's keys in chunks of 32 x KPT; every lane makes ONE probe of
+// each of its KPT keys straight from registers (independent shared-memory loads, 32-bit key halves, a handful of
+// instructions per key): at the loads the table policy allows, three keys in four are settled by it.  The others are
+// parked -- ballot-compacted, no atomics -- in a small warp-private queue as (key, next slot, probes so far); whenever
+// the queue holds a warp's worth, 32 entries are popped, each lane makes one more probe of its entry and re-parks it
+// if it is still unsettled, so no lane ever waits for another lane's probe sequence.
 constexpr int kCount2KPT = 4;
-constexpr int kCount2Rounds = 3;
 constexpr int kCount2Chunk = 32 * kCount2KPT;
-constexpr int kCount2Queue = 1024;          // parked keys per CTA
+constexpr int kCount2Queue = 32 + kCount2Chunk;          // a chunk is only started with fewer than 32 entries parked
 
 template <int THREADS>
 static size_t count_regions2_smem(int log2_region, unsigned nseg) {
-    return ((size_t)12 << log2_region) + sizeof(u64) * kCount2Queue + sizeof(u32) * (2 * nseg + 2);
+    return ((size_t)12 << log2_region) + (size_t)12 * kCount2Queue * (THREADS / 32) + sizeof(u32) * (2 * nseg + 2);
 }
 
-// one complete probe sequence of `key` starting at its home slot (shared-memory table at ks_a / ds_a)
-__device__ __forceinline__ void probe_to_the_end(u32 ks_a, u32 ds_a, u32 rmask, u32 hi_shift, u64 key, u32 &my_new, u32 &overflow) {
-    const u32 home = ((u32)(key >> 32) >> hi_shift) & rmask;
-    u32 off = home;
-    for (;;) {
-        u64 cur = lds_u64(ks_a + off * 8);
-        if (cur == 0) {
-            cur = atoms_cas_u64(ks_a + off * 8, 0ull, key);
-            if (cur == 0) { ++my_new; cur = key; }
-        }
-        if (cur == key) { reds_add_u32(ds_a + off * 4, 1u); return; }
-        off = (off + 1) & rmask;
-        if (off == home) { ++overflow; return; }
+// One probe of key (klo, khi) at slot `off` of the shared-memory region (ks_a: keys, ds_a: count deltas).
+// true: the key was found or inserted and its delta incremented; false: the slot belongs to another key.
+__device__ __forceinline__ bool probe_once(u32 ks_a, u32 ds_a, u32 klo, u32 khi, u32 off, u32 &my_new) {
+    u32 clo, chi;
+    lds_v2(ks_a + off * 8, clo, chi);
+    if (chi == 0) {                          // empty slot (a key's high word holds len + 1 in bits 58..63: never 0): claim it
+        const u64 old = atoms_cas_u64(ks_a + off * 8, 0ull, ((u64)khi << 32) | klo);
+        clo = (u32)old;
+        chi = (u32)(old >> 32);
+        if (chi == 0) { ++my_new; clo = klo; chi = khi; }
     }
+    if (clo == klo && chi == khi) { reds_add_u32(ds_a + off * 4, 1u); return true; }
+    return false;
 }
 
 template <int THREADS>
@@ -581,14 +584,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3)
 count_regions2_kernel(TableView t, RegionParts rp) {
     extern __shared__ __align__(16) u64 dyn_region[];
     __shared__ u32 s_new[THREADS / 32];
-    __shared__ u32 s_qn;
     constexpr u32 W = THREADS / 32;
     const u32 R = 1u << t.log2_region, rmask = R - 1;
     u64 *ks = dyn_region;
     u32 *ds = reinterpret_cast<u32 *>(dyn_region + R);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 *pq = dyn_region + R + R / 2;                                             // parked keys
-    u32 *pre = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + kCount2Queue);   // [nseg + 1] exclusive scan of the segment sizes
+    u64 *qk = dyn_region + R + R / 2 + warp * kCount2Queue;                                     // parked keys of this warp
+    u32 *qo = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + W * kCount2Queue) + warp * kCount2Queue;   // slot | probes << 16
+    u32 *pre = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + W * kCount2Queue) + W * kCount2Queue;    // [nseg + 1] exclusive scan of the segment sizes
     u32 *segoff = pre + (rp.slices << (8 - rp.qbits)) + 1;                        // [nseg] first entry of stream segment k in rp.keys
     const u32 region = blockIdx.x;
     const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
@@ -609,7 +612,7 @@ count_regions2_kernel(TableView t, RegionParts rp) {
             }
             carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (lane == 0) { pre[0] = 0; s_qn = 0; }
+        if (lane == 0) pre[0] = 0;
     }
     const u64 keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
     ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
@@ -621,13 +624,46 @@ count_regions2_kernel(TableView t, RegionParts rp) {
     __syncthreads();
     const u32 total = pre[nseg];
     const u32 hi_shift = (u32)(64 - t.log2_cap) - 32;   // the home slot's region offset lies in the key's high word
-    const u32 ks_a = smem_addr(ks), ds_a = smem_addr(ds), pq_a = smem_addr(pq);
+    const u32 ks_a = smem_addr(ks), ds_a = smem_addr(ds), qk_a = smem_addr(qk), qo_a = smem_addr(qo);
+    const u32 lt_mask = (1u << lane) - 1;
     u32 my_new = 0, overflow = 0, seg = 0;
+    u32 qn = 0;                                          // warp-uniform: parked entries
+    // park one entry per lane with `want` set (ballot-compacted append)
+    auto park = [&](bool want, u32 klo, u32 khi, u32 slot_probes) {
+        const u32 m = __ballot_sync(0xFFFFFFFFu, want);
+        if (want) {
+            const u32 at = qn + __popc(m & lt_mask);
+            sts_u64(qk_a + at * 8, ((u64)khi << 32) | klo);
+            sts_u32(qo_a + at * 4, slot_probes);
+        }
+        qn += __popc(m);
+    };
+    // pop up to 32 entries, one more probe each, re-park what is still unsettled
+    auto serve = [&]() {
+        __syncwarp();
+        const u32 take = min(qn, 32u);
+        const u32 idx = qn - take + lane;
+        u32 klo = 0, khi = 0, sp = 0;
+        const bool mine = lane < take;
+        if (mine) { lds_v2(qk_a + idx * 8, klo, khi); sp = lds_u32(qo_a + idx * 4); }
+        __syncwarp();
+        qn -= take;
+        bool again = false;
+        if (mine) {
+            u32 off = sp & 0xFFFFu;
+            const u32 probes = sp >> 16;
+            if (probes > rmask) ++overflow;              // went around: the region is full
+            else if (!probe_once(ks_a, ds_a, klo, khi, off, my_new)) { again = true; sp = ((off + 1) & rmask) | ((probes + 1) << 16); }
+        }
+        park(again, klo, khi, sp);
+    };
     u64 nk[kCount2KPT];
+    bool full_chunk = false;
     auto load_chunk = [&](u32 c) {
         const u32 i0 = c * kCount2Chunk;
         while (i0 >= pre[seg + 1]) ++seg;                       // warp-uniform: the segment the chunk starts in
-        if (i0 + kCount2Chunk <= pre[seg + 1]) {                // the usual case: the whole chunk lies in one segment
+        full_chunk = i0 + kCount2Chunk <= pre[seg + 1];
+        if (full_chunk) {                                       // the usual case: the whole chunk lies in one segment
             const u64 *src = rp.keys + (segoff[seg] + (i0 - pre[seg])) + lane;
 #pragma unroll
             for (int r = 0; r < kCount2KPT; r++) nk[r] = ld_stream_u64(src + r * 32, drop);
@@ -647,47 +683,28 @@ count_regions2_kernel(TableView t, RegionParts rp) {
     u32 c = warp;
     if (c * kCount2Chunk < total) load_chunk(c);
     while (c * kCount2Chunk < total) {
-        u64 key[kCount2KPT];
-        u32 off[kCount2KPT];
+        u32 klo[kCount2KPT], khi[kCount2KPT];
 #pragma unroll
-        for (int j = 0; j < kCount2KPT; j++) {
-            key[j] = nk[j];
-            off[j] = ((u32)(key[j] >> 32) >> hi_shift) & rmask;
-        }
+        for (int j = 0; j < kCount2KPT; j++) { klo[j] = (u32)nk[j]; khi[j] = (u32)(nk[j] >> 32); }
+        const bool all_valid = full_chunk;
         c += W;
         if (c * kCount2Chunk < total) load_chunk(c);          // in flight during the probes
+        u32 off[kCount2KPT];
+        bool hit[kCount2KPT];
 #pragma unroll
-        for (int r = 0; r < kCount2Rounds; r++) {
-            u64 cur[kCount2KPT];
+        for (int j = 0; j < kCount2KPT; j++) off[j] = (khi[j] >> hi_shift) & rmask;
+        if (all_valid) {
 #pragma unroll
-            for (int j = 0; j < kCount2KPT; j++) cur[j] = key[j] != 0 ? lds_u64(ks_a + off[j] * 8) : 1ull;
+            for (int j = 0; j < kCount2KPT; j++) hit[j] = probe_once(ks_a, ds_a, klo[j], khi[j], off[j], my_new);
+        } else {
 #pragma unroll
-            for (int j = 0; j < kCount2KPT; j++) {
-                if (key[j] != 0) {
-                    if (cur[j] == 0) {                       // empty slot: claim it
-                        cur[j] = atoms_cas_u64(ks_a + off[j] * 8, 0ull, key[j]);
-                        if (cur[j] == 0) { ++my_new; cur[j] = key[j]; }
-                    }
-                    if (cur[j] == key[j]) { reds_add_u32(ds_a + off[j] * 4, 1u); key[j] = 0; }
-                    else off[j] = (off[j] + 1) & rmask;
-                }
-            }
+            for (int j = 0; j < kCount2KPT; j++) hit[j] = khi[j] == 0 || probe_once(ks_a, ds_a, klo[j], khi[j], off[j], my_new);
         }
-        // park what is left (a key restarts from its home slot later: the probes it repeats all hit occupied slots)
 #pragma unroll
-        for (int j = 0; j < kCount2KPT; j++) {
-            if (key[j] != 0) {
-                const u32 pos = atomicAdd(&s_qn, 1u);
-                if (pos < (u32)kCount2Queue) sts_u64(pq_a + pos * 8, key[j]);
-                else probe_to_the_end(ks_a, ds_a, rmask, hi_shift, key[j], my_new, overflow);
-            }
-        }
+        for (int j = 0; j < kCount2KPT; j++) park(!hit[j], klo[j], khi[j], ((off[j] + 1) & rmask) | (1u << 16));
+        while (qn >= 32) serve();
     }
-    __syncthreads();
-    {
-        const u32 nq = min(s_qn, (u32)kCount2Queue);
-        for (u32 i = threadIdx.x; i < nq; i += THREADS) probe_to_the_end(ks_a, ds_a, rmask, hi_shift, lds_u64(pq_a + i * 8), my_new, overflow);
-    }
+    while (qn > 0) serve();
     __syncthreads();
     for (u32 i = threadIdx.x; i < R; i += THREADS) {
         const u32 d = ds[i];
@@ -1139,6 +1156,7 @@ static int run_gated(ssq_counter *c, int64_t n, Launch launch) {
         SSQ_CUDA(cudaMemcpyAsync(c->h_gate, c->d_gate, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
         SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, st));
         SSQ_CUDA(cudaStreamSynchronize(st));
+        c->known_size = (int64_t)*c->h_size;
         if (c->h_gate[0] == 0) break;
         pos += (int64_t)c->h_gate[1] * sub;
         // room for what is there plus the rest of this batch, at least x4
@@ -1340,9 +1358,25 @@ static int finish_pass(ssq_counter *c) {
     ssq_ctx *ctx = c->ctx;
     SSQ_CUDA(cudaMemcpyAsync(c->h_size, c->d_size, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    c->known_size = (int64_t)*c->h_size;
     const int64_t cap = (int64_t)1 << c->log2_cap;
     if ((int64_t)*c->h_size > cap - cap / 4 - cap / 8 - cap / 40) return grow(c, c->log2_cap + 1);
     return SSQ_OK;
+}
+
+// Before a bounded single pass of n keys: make room.  The pass can create at most n keys and, if the caller's bound
+// holds, at most expected_unique - size of them; when that many would load the table beyond 75 % the table grows FIRST
+// (a pass cannot grow the table while it runs, and a full region drops keys).  A table that already holds MORE keys
+// than the bound has proven the bound wrong: the counter switches to the conservative gated mode for good
+// (expected_unique = 0), which grows whenever it has to.  A bound that holds never triggers either.
+static int make_room(ssq_counter *c, int64_t n) {
+    if (c->known_size > c->expected_unique) { c->expected_unique = 0; return SSQ_OK; }
+    const int64_t cap = (int64_t)1 << c->log2_cap;
+    int64_t ub = c->expected_unique - c->known_size;
+    if (n < ub) ub = n;
+    if (c->known_size + ub <= cap - cap / 4) return SSQ_OK;
+    SSQ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return grow(c, log2_cap_for(c->known_size + ub));
 }
 
 // Fused pack+count of reads whose bytes are ascii[lo, hi) (ascii may be a virtual base pointer);
@@ -1351,12 +1385,15 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
                     int64_t index_base, u64 *words, uint8_t *lens) {
     ssq_ctx *ctx = c->ctx;
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
-    if (c->expected_unique <= 0)
+    int rc = SSQ_OK;
+    if (c->expected_unique > 0 && (rc = make_room(c, n)) != SSQ_OK) return rc;
+    if (c->expected_unique <= 0) {
+        c->last_pass_phases = 0;
         return run_gated(c, n, [&](int64_t p, int64_t cnt, const u64 *stop) -> int {
             return launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets + p, cnt, index_base + p,
                                      words + (size_t)p * W, lens + p, view_of(c), PartView{}, stop);
         });
-    int rc;
+    }
     SSQ_CUDA(cudaEventRecord(c->ev[0], ctx->stream));
     if (use_deferred(c, n)) {
         c->last_pass_phases = 2;
@@ -1410,6 +1447,7 @@ int ssq_counter_create(ssq_ctx *ctx, int klass, int64_t expected_unique, int has
     c->region_count = nullptr;
     c->region_base = nullptr;
     c->expected_unique = expected_unique;
+    c->known_size = 0;
     c->part_keys = nullptr;
     c->part_cursor = nullptr;
     c->part_cap = 0;
@@ -1462,6 +1500,7 @@ int ssq_counter_clear(ssq_counter *c) {
     const size_t nslots = (size_t)1 << c->log2_cap;
     SSQ_CUDA(cudaMemsetAsync(c->slots, 0, nslots * slot_bytes(c->klass), c->ctx->stream));
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), c->ctx->stream));
+    c->known_size = 0;
     if (c->first_idx) SSQ_CUDA(cudaMemsetAsync(c->first_idx, 0xFF, nslots * sizeof(u64), c->ctx->stream));
     if (c->region_count)
         SSQ_CUDA(cudaMemsetAsync(c->region_count, 0, (nslots >> region_bits_for(c->log2_cap)) * sizeof(u32), c->ctx->stream));
@@ -1475,6 +1514,10 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
+    if (c->expected_unique > 0) {
+        int rc0 = make_room(c, n);
+        if (rc0) return rc0;
+    }
     if (c->expected_unique > 0) {
         int rc = SSQ_OK;
         if (counts == nullptr && c->klass == SSQ_CLASS_64 && use_deferred(c, n)) {
@@ -1554,6 +1597,12 @@ int ssq_counter_merge_regions(ssq_counter *c, const uint64_t *words, const uint8
     if (!ok) return insert_common(c, words, lens, counts, n);     // the region grids do not nest: plain weighted insert
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
+    {
+        const int before = c->log2_cap;
+        int rc0 = make_room(c, n);
+        if (rc0) return rc0;
+        if (c->log2_cap != before || c->expected_unique <= 0) return insert_common(c, words, lens, counts, n);   // the region grid changed under the blocks / bound given up
+    }
     const size_t bytes = (size_t)16 << lr;
     int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
     if (rc) return rc;

@@ -46,6 +46,7 @@ struct ssq_counter {
     ssq::u64 *d_gate;     // {stop flag, first stopped sub-batch} (device, see run_gated)
     ssq::u64 *h_gate;     // pinned
     int64_t expected_unique;   // caller's bound on the distinct keys (0 = unknown: conservative gated inserts)
+    int64_t known_size;        // occupied slots as of the last host read-back (finish_pass / run_gated / clear / grow)
     ssq::u64 *part_keys;       // partition buffers of the deferred-insert path (lazily sized)
     ssq::u32 *part_cursor;     // [part_ctas][kParts] segment fill counts
     int64_t part_cap;          // key entries currently allocated

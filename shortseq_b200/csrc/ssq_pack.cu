@@ -446,6 +446,189 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     }
 }
 
+// ---- ShortSeq64, uniform batches of 32-nt reads ----------------------------------------------------
+// The C2 shape (1e9 x 32 nt): offsets[i] = offsets[0] + 32 i and the first base sits on a 16-byte address boundary.
+// pack_fixed_kernel spends most of its instructions on what such a batch does not need (tile geometry, a code stream in
+// shared memory, per-read extraction, 64-bit offset arithmetic).  Here a WARP owns tiles of 64 reads = 2048 contiguous
+// bytes = four fully coalesced 512-byte loads (a lane's 16-byte chunk j is half (lane & 1) of read 16 j + lane / 2);
+// the chunks are encoded in registers, neighbouring lanes swap halves with two shuffles and every lane ends up with two
+// whole reads.  The tile's 65 offsets are checked against the arithmetic progression by the same warp (a vote, no
+// barrier); a tile that fails the check, and the ragged last tile, take a plain lane-per-read path with the general
+// kernel's semantics.  The CTA only synchronises to flush the staging rings.  The host picks this kernel when the
+// batch holds exactly 32 n bytes (launch_fixed); everything else is decided here, tile by tile.
+constexpr int kWarpTileReads = 64;
+constexpr int kPack32FlushEvery = 4;        // warp tiles between two flushes: 8 warps x 4 x 64 = 2048 keys, as pack_fixed_kernel
+
+// One read the slow way (any length, any alignment): returns false when the read must not be counted.
+__device__ __noinline__ bool pack32_slow_read(const PackArgs &a, int64_t i, u64 &word, u32 &len_out) {
+    const int64_t o0 = a.offsets[i], o1 = a.offsets[i + 1];
+    const int64_t len = o1 - o0;
+    word = 0;
+    len_out = 0;
+    if (o0 < a.lo || o1 > a.hi || len < 0) { atomicMin(&a.rep->first_bad_len, (u64)(a.index_base + i)); a.words[i] = 0; ((uint8_t *)a.lens)[i] = 0; return false; }
+    if (len > 32) { report_len(a.rep, len, (u64)(a.index_base + i)); a.words[i] = 0; ((uint8_t *)a.lens)[i] = 0; return false; }
+    bool bad = false;
+    for (int k = 0; k < (int)len; k++) {
+        const u32 ch = a.ascii[o0 + k];
+        bad |= !is_acgt((uint8_t)ch);
+        word |= (u64)((ch >> 1) & 3u) << (2 * k);
+    }
+    a.words[i] = word;
+    ((uint8_t *)a.lens)[i] = (uint8_t)len;
+    len_out = (u32)len;
+    if (bad) atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + i));
+    return !bad;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+    extern __shared__ __align__(16) u64 dyn_ring[];
+    __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
+    __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
+    __shared__ u32 s_new[kPackThreads / 32];
+    __shared__ u32 s_unstaged_new;
+    const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
+    u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
+    if (MODE != kModePack && stop != nullptr && *stop != 0) return;
+    if (MODE == kModeScatter) {
+        stager_init(stg);
+        if (threadIdx.x == 0) s_unstaged_new = 0;
+        __syncthreads();
+    }
+    constexpr int kWarps = kPackThreads / 32;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool odd = lane & 1;
+    const int64_t ntiles = (a.n + kWarpTileReads - 1) / kWarpTileReads;
+    const int64_t wstride = (int64_t)gridDim.x * kWarps;
+    const int64_t cta_first = (int64_t)blockIdx.x * kWarps;
+    const int iters = cta_first < ntiles ? (int)((ntiles - cta_first + wstride - 1) / wstride) : 0;   // trip count of warp 0: CTA-uniform
+    const int64_t o0 = a.offsets[0];
+    const uint8_t *const base = a.ascii + o0;                 // read i starts at base + 32 i in a uniform batch
+    const bool aligned = ((uintptr_t)base & 15) == 0 && ((uintptr_t)a.lens & 15) == 0 && o0 >= a.lo;
+    u32 my_new = 0;
+
+    // prefetch state of the next tile: its four chunks and the offsets this lane checks
+    uint4 v[4];
+    int64_t chk[3];
+    bool pre_full = false;
+    auto prefetch = [&](int64_t wt) {
+        const int64_t first = wt * kWarpTileReads;
+        pre_full = wt < ntiles && aligned && first + kWarpTileReads <= a.n && o0 + 32 * (first + kWarpTileReads) <= a.hi;
+        if (pre_full) {
+            const uint8_t *src = base + 32 * first + 16 * lane;
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = ld_stream_v4(src + 512 * j);
+            chk[0] = a.offsets[first + lane];
+            chk[1] = a.offsets[first + 32 + lane];
+            chk[2] = lane == 0 ? a.offsets[first + kWarpTileReads] : 0;
+        }
+    };
+    int64_t wt = cta_first + warp;
+    prefetch(wt);
+    for (int it = 0; it < iters; it++, wt += wstride) {
+        const int64_t first = wt * kWarpTileReads;
+        bool fast = pre_full;
+        u32 fc[4];
+        u32 bad = 0;
+        if (fast) {
+            const int64_t e0 = o0 + 32 * (first + lane);
+            bool uni = chk[0] == e0 && chk[1] == e0 + 32 * 32 && (lane != 0 || chk[2] == e0 + 32 * kWarpTileReads);
+            fast = __all_sync(0xFFFFFFFFu, uni);
+#pragma unroll
+            for (int j = 0; j < 4; j++) fc[j] = encode16(v[j], bad);
+        }
+        prefetch(wt + wstride);
+        if (fast) {
+            // lanes 2m / 2m+1 hold the low / high half of read 16 j + m in fc[j]; the even lane assembles the reads of
+            // j = 0, 1 (reads m, 16 + m), the odd lane those of j = 2, 3 (reads 32 + m, 48 + m)
+            const u32 x0 = __shfl_xor_sync(0xFFFFFFFFu, odd ? fc[0] : fc[2], 1);
+            const u32 x1 = __shfl_xor_sync(0xFFFFFFFFu, odd ? fc[1] : fc[3], 1);
+            u64 w2[2];
+            w2[0] = odd ? ((u64)fc[2] << 32) | x0 : ((u64)x0 << 32) | fc[0];
+            w2[1] = odd ? ((u64)fc[3] << 32) | x1 : ((u64)x1 << 32) | fc[1];
+            const u32 r0 = (lane >> 1) + (odd ? 32u : 0u);               // reads r0 and r0 + 16 of the tile
+            bool ok2[2] = {true, true};
+            if (__any_sync(0xFFFFFFFFu, bad != 0)) {                      // some byte of the tile is invalid: exact re-check
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int64_t i = first + r0 + 16 * q;
+                    if (read_has_bad_base(base + 32 * i, 32)) {
+                        ok2[q] = false;
+                        atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + i));
+                    }
+                }
+            }
+            u64 *wdst = a.words + first + r0;
+            wdst[0] = w2[0];
+            wdst[16] = w2[1];
+            if (lane < kWarpTileReads / 16)
+                reinterpret_cast<uint4 *>((uint8_t *)a.lens + first)[lane] = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (MODE == kModeDirect && ok2[q]) {
+                    bool is_new = false;
+                    insert64(t, w2[q], 32u, 1ull, is_new);
+                    my_new += is_new ? 1u : 0u;
+                }
+                if constexpr (MODE == kModeScatter) {
+                    if (ok2[q]) {
+                        const u64 h2 = rotl64(mix64(w2[q]), t.rot);
+                        const u64 key = key64_of(h2, 32u);
+                        if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
+                    }
+                }
+            }
+        } else if (wt < ntiles) {
+            // a tile that is not 64 aligned 32-nt reads (or the ragged end of the batch): lane-per-read
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                const int64_t i = first + lane + 32 * q;
+                if (i >= a.n) continue;
+                u64 word;
+                u32 len;
+                if (!pack32_slow_read(a, i, word, len)) continue;
+                if (MODE == kModeDirect) {
+                    bool is_new = false;
+                    insert64(t, word, len, 1ull, is_new);
+                    my_new += is_new ? 1u : 0u;
+                }
+                if constexpr (MODE == kModeScatter) {
+                    const u64 h2 = rotl64(mix64(word), t.rot);
+                    const u64 key = key64_of(h2, len);
+                    if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
+                }
+            }
+        }
+        if constexpr (MODE == kModeScatter) {
+            if ((it % kPack32FlushEvery) == kPack32FlushEvery - 1) {
+                __syncthreads();
+                flush_lines<false, 1>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                __syncthreads();
+            }
+        }
+    }
+    if constexpr (MODE == kModeScatter) {
+        __syncthreads();
+        flush_lines<true, 1>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+        __syncthreads();
+        for (int p = threadIdx.x; p < kParts; p += kPackThreads)
+            pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
+        if (threadIdx.x == 0) my_new += s_unstaged_new;
+    }
+    if (MODE != kModePack) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+        if (lane == 0) s_new[warp] = my_new;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 tot = 0;
+            for (int k = 0; k < kWarps; k++) tot += s_new[k];
+            if (tot) atomicAdd(t.size, tot);
+        }
+    }
+}
+
 // ---- ShortSeqVar: one warp per read, lane j owns word j ----------------------------------
 constexpr int kVarTileReads = 32;
 constexpr int kVarMaxChunks = (kVarTileReads * 1024 + 30) / 16 + 1;
@@ -532,9 +715,42 @@ static int fixed_grid(ssq_ctx *ctx, int64_t n) {
     return grid_for(ctx, (n + kTileReads - 1) / kTileReads, per_sm);
 }
 
+// A batch of exactly 32 n bytes whose first byte is 16-byte aligned is (almost certainly) n reads of 32 nt: such
+// batches go to pack32_kernel, which verifies the offsets tile by tile and handles anything else it meets.
+static bool looks_uniform32(const PackArgs &a) {
+    static const bool off = getenv("SSQ_NO_PACK32") != nullptr;        // development: force the general kernel
+    return !off && a.n >= 4096 && a.hi - a.lo == 32 * a.n && (((uintptr_t)a.ascii + (uintptr_t)a.lo) & 15) == 0;
+}
+
+template <int MODE>
+static int launch_pack32(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid) {
+    static bool done = false;
+    static int done_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (MODE == kModeScatter && (!done || done_dev != dev)) {
+        SSQ_CUDA(cudaFuncSetAttribute(pack32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE>()));
+        SSQ_CUDA(cudaFuncSetAttribute(pack32_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        done = true;
+        done_dev = dev;
+    }
+    if (grid <= 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack32_kernel<MODE>, kPackThreads, pack_dyn_smem<MODE>()) != cudaSuccess || per_sm < 1)
+            per_sm = 3;
+        grid = grid_for(ctx, (a.n + kTileReads - 1) / kTileReads, per_sm);
+    }
+    pack32_kernel<MODE><<<grid, kPackThreads, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
 template <int KLASS, int MODE>
 static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid = 0) {
     if (a.n <= 0) return SSQ_OK;
+    if constexpr (KLASS == SSQ_CLASS_64) {
+        if (looks_uniform32(a)) return launch_pack32<MODE>(ctx, a, t, pv, stop, grid);
+    }
     if (grid <= 0) grid = fixed_grid<KLASS, MODE>(ctx, a.n);
     int rc = prepare_fixed_kernel<KLASS, MODE>();
     if (rc) return rc;

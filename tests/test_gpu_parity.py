@@ -392,6 +392,44 @@ def test_counter_region_path_table_sizes(sq, oracle, log2_slots):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
 
 
+def test_counter_bound_exceeded_across_batches(sq, oracle):
+    """expected_unique = 40000 gives 2^17 slots; two batches of 70000 distinct keys each do not fit.  The
+    table must grow (before the second batch: it already holds more keys than the bound) instead of dropping keys."""
+    rng = np.random.default_rng(5)
+    ctr = sq.DeviceCounter(0, expected_unique=40_000)
+    assert ctr.capacity() == 1 << 17
+    total = {}
+    for batch in range(3):
+        reads = rand_reads(rng, 70_000, 28, 32)
+        buf, off = concat(reads)
+        ow, ol, _ = oracle.pack_batch(0, buf, off)
+        uw, ul, uc, _ = oracle.count(ow, ol, 1)
+        for k, v in counter_dict(uw, ul, uc).items():
+            total[k] = total.get(k, 0) + v
+        ctr.pack_count(buf, off)
+        assert len(ctr) == len(total)
+    assert ctr.capacity() >= 1 << 19
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == total
+    # the same through insert() of packed batches, and a bound that grows the table before the pass
+    ctr2 = sq.DeviceCounter(0, expected_unique=100_000)            # 2^18 slots; the bound holds, 3 x 70000 reads of 90000 keys
+    pool = rand_reads(rng, 90_000, 20, 32)
+    tot2 = {}
+    for batch in range(3):
+        reads = [pool[i] for i in rng.integers(0, len(pool), size=70_000)]
+        buf, off = concat(reads)
+        ow, ol, _ = oracle.pack_batch(0, buf, off)
+        uw, ul, uc, _ = oracle.count(ow, ol, 1)
+        for k, v in counter_dict(uw, ul, uc).items():
+            tot2[k] = tot2.get(k, 0) + v
+        ctr2.insert(sq.pack_batch(buf, off, klass=0))
+    assert ctr2.capacity() == 1 << 18
+    keys, counts, _, _ = ctr2.export(1)
+    kw, kl, _ = keys.to_host()
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == tot2
+
+
 @pytest.mark.parametrize("log2_slots", [28, 29])
 def test_counter_bench_geometry(sq, oracle, log2_slots):
     """The geometry bench.py's headline runs on: DeviceCounter(expected_unique = 1e8) -> 2^28 slots =
