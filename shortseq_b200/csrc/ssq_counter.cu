@@ -370,10 +370,15 @@ __global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t,
         for (int j = 0; j < kScatterRounds; j++) k[j] = nk[j];
         unflushed += have;
         have = load_tile();                      // in flight while this tile is staged and flushed
+        {
+            u32 part[kScatterRounds];
+            bool valid[kScatterRounds], ok[kScatterRounds];
 #pragma unroll
-        for (int j = 0; j < kScatterRounds; j++) {
-            if (k[j] == 0) continue;
-            if (!stage_key(stg, (u32)(k[j] >> 48) & 0xFFu, k[j])) insert_unstaged(t, k[j], p, &s_unstaged_new);
+            for (int j = 0; j < kScatterRounds; j++) { part[j] = (u32)(k[j] >> 48) & 0xFFu; valid[j] = k[j] != 0; }
+            stage_keys<kScatterRounds>(stg, part, k, valid, ok);
+#pragma unroll
+            for (int j = 0; j < kScatterRounds; j++)
+                if (!ok[j]) insert_unstaged(t, k[j], p, &s_unstaged_new);
         }
         if (unflushed >= flush_keys || !have) {   // flush once enough keys are staged (a short tail tile waits for the next one)
             unflushed = 0;
@@ -1178,7 +1183,7 @@ static bool use_deferred(const ssq_counter *c, int64_t n) {
     return table_bytes > kDirectTableBytes && n >= ((int64_t)1 << c->log2_cap) / 4;
 }
 
-int scatter_grid(ssq_ctx *ctx, int klass, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
+int scatter_grid(ssq_ctx *ctx, int klass, const uint8_t *ascii, int64_t lo, int64_t hi, int64_t n);   // ssq_pack.cu: grid of the fused pack+scatter launch
 
 // development tunables (read once per process)
 static int env_int(const char *name, int dflt, int lo, int hi) {
@@ -1398,7 +1403,7 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
     if (use_deferred(c, n)) {
         c->last_pass_phases = 2;
         PartView pv;
-        int sgrid = scatter_grid(ctx, c->klass, n);
+        int sgrid = scatter_grid(ctx, c->klass, ascii, lo, hi, n);
         if ((int64_t)sgrid * 65536 > n) sgrid = (int)(n / 65536 > 0 ? n / 65536 : 1);   // keep the segments from being mostly padding
         rc = prepare_parts(c, n, sgrid, &pv);
         if (rc) return rc;

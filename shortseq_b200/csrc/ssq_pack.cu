@@ -480,13 +480,13 @@ __device__ __noinline__ bool pack32_slow_read(const PackArgs &a, int64_t i, u64 
     return !bad;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) pack32_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
-    __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
-    __shared__ u32 s_new[kPackThreads / 32];
+    __shared__ u32 s_list[MODE == kModeScatter ? (THREADS / 32) * 64 : 1];
+    __shared__ u32 s_new[THREADS / 32];
     __shared__ u32 s_unstaged_new;
     const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
     u64 *const seg0 = MODE == kModeScatter ? pv.keys + (size_t)blockIdx.x * kParts * pv.seg_cap : nullptr;
@@ -496,7 +496,8 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, Tab
         if (threadIdx.x == 0) s_unstaged_new = 0;
         __syncthreads();
     }
-    constexpr int kWarps = kPackThreads / 32;
+    constexpr int kWarps = THREADS / 32;
+    constexpr int kFlushEvery = kPack32FlushEvery * 8 / kWarps;          // 2048 keys between two flushes whatever the CTA size
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool odd = lane & 1;
     const int64_t ntiles = (a.n + kWarpTileReads - 1) / kWarpTileReads;
@@ -564,20 +565,30 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, Tab
             wdst[16] = w2[1];
             if (lane < kWarpTileReads / 16)
                 reinterpret_cast<uint4 *>((uint8_t *)a.lens + first)[lane] = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+            if constexpr (MODE == kModeDirect) {
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                if (MODE == kModeDirect && ok2[q]) {
-                    bool is_new = false;
-                    insert64(t, w2[q], 32u, 1ull, is_new);
-                    my_new += is_new ? 1u : 0u;
-                }
-                if constexpr (MODE == kModeScatter) {
+                for (int q = 0; q < 2; q++) {
                     if (ok2[q]) {
-                        const u64 h2 = rotl64(mix64(w2[q]), t.rot);
-                        const u64 key = key64_of(h2, 32u);
-                        if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
+                        bool is_new = false;
+                        insert64(t, w2[q], 32u, 1ull, is_new);
+                        my_new += is_new ? 1u : 0u;
                     }
                 }
+            }
+            if constexpr (MODE == kModeScatter) {
+                u64 h2[2], key[2];
+                u32 part[2];
+                bool staged[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    h2[q] = rotl64(mix64(w2[q]), t.rot);
+                    key[q] = key64_of(h2[q], 32u);
+                    part[q] = (u32)(h2[q] >> 56);
+                }
+                stage_keys<2>(stg, part, key, ok2, staged);
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                    if (!staged[q]) insert64_slow(t, h2[q], key[q], &s_unstaged_new);
             }
         } else if (wt < ntiles) {
             // a tile that is not 64 aligned 32-nt reads (or the ragged end of the batch): lane-per-read
@@ -601,7 +612,7 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, Tab
             }
         }
         if constexpr (MODE == kModeScatter) {
-            if ((it % kPack32FlushEvery) == kPack32FlushEvery - 1) {
+            if ((it % kFlushEvery) == kFlushEvery - 1) {
                 __syncthreads();
                 flush_lines<false, 1>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
                 __syncthreads();
@@ -612,7 +623,7 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack32_kernel(PackArgs a, Tab
         __syncthreads();
         flush_lines<true, 1>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
         __syncthreads();
-        for (int p = threadIdx.x; p < kParts; p += kPackThreads)
+        for (int p = threadIdx.x; p < kParts; p += THREADS)
             pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
         if (threadIdx.x == 0) my_new += s_unstaged_new;
     }
@@ -717,30 +728,46 @@ static int fixed_grid(ssq_ctx *ctx, int64_t n) {
 
 // A batch of exactly 32 n bytes whose first byte is 16-byte aligned is (almost certainly) n reads of 32 nt: such
 // batches go to pack32_kernel, which verifies the offsets tile by tile and handles anything else it meets.
-static bool looks_uniform32(const PackArgs &a) {
+static bool looks_uniform32(const uint8_t *ascii, int64_t lo, int64_t hi, int64_t n) {
     static const bool off = getenv("SSQ_NO_PACK32") != nullptr;        // development: force the general kernel
-    return !off && a.n >= 4096 && a.hi - a.lo == 32 * a.n && (((uintptr_t)a.ascii + (uintptr_t)a.lo) & 15) == 0;
+    return !off && n >= 4096 && hi - lo == 32 * n && (((uintptr_t)ascii + (uintptr_t)lo) & 15) == 0;
 }
 
-template <int MODE>
-static int launch_pack32(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid) {
+static int pack32_threads() {
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("SSQ_PACK32_THREADS"); v = e && atoi(e) == 512 ? 512 : 256; }
+    return v;
+}
+
+template <int MODE, int THREADS>
+static int pack32_grid(ssq_ctx *ctx, int64_t n) {
     static bool done = false;
     static int done_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (MODE == kModeScatter && (!done || done_dev != dev)) {
-        SSQ_CUDA(cudaFuncSetAttribute(pack32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE>()));
-        SSQ_CUDA(cudaFuncSetAttribute(pack32_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (cudaFuncSetAttribute(pack32_kernel<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE>()) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(pack32_kernel<MODE, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return 0;
         done = true;
         done_dev = dev;
     }
-    if (grid <= 0) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack32_kernel<MODE>, kPackThreads, pack_dyn_smem<MODE>()) != cudaSuccess || per_sm < 1)
-            per_sm = 3;
-        grid = grid_for(ctx, (a.n + kTileReads - 1) / kTileReads, per_sm);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack32_kernel<MODE, THREADS>, THREADS, pack_dyn_smem<MODE>()) != cudaSuccess || per_sm < 1)
+        per_sm = THREADS == 512 ? 2 : 3;
+    return grid_for(ctx, (n * 32 + (int64_t)THREADS * 64 - 1) / ((int64_t)THREADS * 64), per_sm);
+}
+
+template <int MODE>
+static int launch_pack32(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid) {
+    if (pack32_threads() == 512) {
+        const int g = pack32_grid<MODE, 512>(ctx, a.n);
+        if (g <= 0) { set_error("pack32_kernel: cannot configure shared memory"); return SSQ_ERR_CUDA; }
+        pack32_kernel<MODE, 512><<<grid > 0 ? grid : g, 512, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
+    } else {
+        const int g = pack32_grid<MODE, 256>(ctx, a.n);
+        if (g <= 0) { set_error("pack32_kernel: cannot configure shared memory"); return SSQ_ERR_CUDA; }
+        pack32_kernel<MODE, 256><<<grid > 0 ? grid : g, 256, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
     }
-    pack32_kernel<MODE><<<grid, kPackThreads, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -749,7 +776,7 @@ template <int KLASS, int MODE>
 static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, const PartView &pv, const u64 *stop, int grid = 0) {
     if (a.n <= 0) return SSQ_OK;
     if constexpr (KLASS == SSQ_CLASS_64) {
-        if (looks_uniform32(a)) return launch_pack32<MODE>(ctx, a, t, pv, stop, grid);
+        if (looks_uniform32(a.ascii, a.lo, a.hi, a.n)) return launch_pack32<MODE>(ctx, a, t, pv, stop, grid);
     }
     if (grid <= 0) grid = fixed_grid<KLASS, MODE>(ctx, a.n);
     int rc = prepare_fixed_kernel<KLASS, MODE>();
@@ -759,8 +786,12 @@ static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, con
     return SSQ_OK;
 }
 
-// grid of the scatter-mode launch for n reads: it fixes the segment layout of the partition buffers
-int scatter_grid(ssq_ctx *ctx, int klass, int64_t n) {
+// grid of the scatter-mode launch for the n reads in ascii[lo, hi): it fixes the segment layout of the partition buffers
+int scatter_grid(ssq_ctx *ctx, int klass, const uint8_t *ascii, int64_t lo, int64_t hi, int64_t n) {
+    if (klass == SSQ_CLASS_64 && looks_uniform32(ascii, lo, hi, n)) {
+        const int g = pack32_threads() == 512 ? pack32_grid<kModeScatter, 512>(ctx, n) : pack32_grid<kModeScatter, 256>(ctx, n);
+        if (g > 0) return g;
+    }
     return klass == SSQ_CLASS_64 ? fixed_grid<SSQ_CLASS_64, kModeScatter>(ctx, n) : fixed_grid<SSQ_CLASS_192, kModeScatter>(ctx, n);
 }
 

@@ -261,6 +261,23 @@ __device__ __forceinline__ bool stage_key(const Stager &s, u32 part, u64 key) {
     return true;
 }
 
+// stage_key for N keys at once: the N shared-memory atomics are issued back to back, then the N tail reads, then the N
+// stores, so their latencies overlap instead of adding up (each step of stage_key waits for the one before it).
+// valid[j] = false skips key j; ok[j] = false on return: ring full, the caller inserts key j directly.
+template <int N>
+__device__ __forceinline__ void stage_keys(const Stager &s, const u32 (&part)[N], const u64 (&key)[N], const bool (&valid)[N], bool (&ok)[N]) {
+    u32 pos[N], tl[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) pos[j] = valid[j] ? atoms_add_u32(s.head + 4 * part[j], 1u) : 0u;
+#pragma unroll
+    for (int j = 0; j < N; j++) tl[j] = valid[j] ? lds_u32(s.tail + 4 * part[j]) : 0u;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        ok[j] = !valid[j] || pos[j] - tl[j] < (u32)kRingKeys;
+        if (valid[j] && ok[j]) sts_u64(s.ring + 8 * (part[j] * kRingKeys + (pos[j] & (kRingKeys - 1))), key[j]);
+    }
+}
+
 // Keys that find no room in their segment are counted right away.  `fixed_top` >= 0: the top 8 hash bits of
 // every key of this CTA (second-level scatter); < 0: the partition index is the top 8 bits (first level).
 static __device__ __noinline__ void insert_unstaged(const TableView &t, u64 key, u32 top, u32 *my_new) {
