@@ -566,7 +566,7 @@ def cfg_c4(sq, args, peak):
 
     def decode():
         _lib.check(lib.ssq_lens_to_offsets(h, ptr(vlens), 2, n, ptr(out_off)))
-        _lib.check(lib.ssq_decodevar(h, ptr(words), ptr(word_off), ptr(vlens), n, ptr(out), ptr(out_off)))
+        _lib.check(lib.ssq_decodevar(h, ptr(words), ptr(word_off), ptr(vlens), n, ptr(out_off), ptr(out)))
 
     pack_ms = timed(pack, 3, 2)
     rep = ctx.sync()
@@ -811,8 +811,9 @@ def run_ours(args):
         d["frac"] = round(d["achieved_gbs"] / peak, 4) if bytes_ else None
         return d
 
+    pack_name = "ssq::pack32_kernel<{mode},256>" if (klass == sq.CLASS_64 and L == 32) else f"ssq::pack_fixed_kernel<{W // 3},{{mode}}>"
     if deferred:
-        kernels = [kern(f"ssq::pack_fixed_kernel<{W // 3},2>", "pack + validate + scatter keys to 256 hash partitions", p_ms[0], pack_bytes)]
+        kernels = [kern(pack_name.format(mode=2), "pack + validate + scatter keys to 256 hash partitions", p_ms[0], pack_bytes)]
         if regions:
             kernels.append(kern("ssq::region_scatter_kernel", "route keys to their 4096-slot table region (second 256-way scatter); "
                                 "shares the count phase's algorithmic bytes with the region count", p_ms[1], 0))
@@ -823,7 +824,7 @@ def run_ours(args):
         else:
             kernels.append(kern("ssq::count_parts_kernel", "partition-ordered table insertion (L2-resident table ranges)", p_ms[2], count_bytes))
     else:
-        kernels = [kern(f"ssq::pack_fixed_kernel<{W // 3},1>", "pack + validate + insert", p_ms[0], alg_bytes)]
+        kernels = [kern(pack_name.format(mode=1), "pack + validate + insert", p_ms[0], alg_bytes)]
     dom = max(kernels, key=lambda kk: kk["ms_per_launch"])
     # top level = the dominant kernel (most device time per step); "pass" = all kernels of one ssq_counter_pack_count
     roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],

@@ -266,6 +266,30 @@ int ssq_host_fastq_count(ssq_ctx *ctx, ssq_counter *c64, ssq_counter *c192, cons
                          int64_t chunk_bytes, int track_first_index, int64_t *n_reads, int64_t *n_longer,
                          int64_t *first_longer, ssq_report *report);
 
+/* ---- batched slicing, k-mers, tolerant alphabet ------
+ * Replace, for whole arrays, the reference's per-object slice constructors (short_seq.pyx:94-116 _slice,
+ * :119-199 _slice_to_ShortSeq64/192/Var, :202-238 _shift_copy_trim: funnel-shift the blocks, trim the tail).
+ * A packed array is (klass, words, word_off, lens): word_off only for SSQ_CLASS_VAR (lens uint16 then, else uint8).
+ * ssq_slice: out[i] = in[i][start_i : stop_i], both clamped to the read like Python's slices (the caller resolves
+ * negative indices) and to `width` bases.  starts / stops are per-read int64 arrays, or NULL for the scalars
+ * start0 / stop0.  out_klass must hold `width` bases (SSQ_CLASS_64: <= 32, SSQ_CLASS_192: <= 96, else SSQ_CLASS_VAR:
+ * its out_word_off[n+1] comes from ssq_slice_words, out_lens is uint16).  Results are tail-trimmed: bits >= 2 len are 0. */
+int ssq_slice_words(ssq_ctx *ctx, int in_klass, const void *lens, int64_t n, const int64_t *starts, const int64_t *stops,
+                    int64_t start0, int64_t stop0, int32_t width, int64_t *out_word_off);
+int ssq_slice(ssq_ctx *ctx, int in_klass, const uint64_t *words, const int64_t *word_off, const void *lens, int64_t n,
+              const int64_t *starts, const int64_t *stops, int64_t start0, int64_t stop0, int32_t width, int out_klass,
+              uint64_t *out_words, const int64_t *out_word_off, void *out_lens);
+/* Every k-mer (1 <= k <= 32, every `stride`-th start) of every read as a ShortSeq64 word, grouped by read:
+ * ssq_kmers_count fills kmer_off[n+1] (exclusive scan of (len - k) / stride + 1 for reads of at least k bases),
+ * ssq_kmers64 writes kmer_off[n] words and lengths (= k).  Counting them with ssq_counter_insert is k-mer counting. */
+int ssq_kmers_count(ssq_ctx *ctx, int in_klass, const void *lens, int64_t n, int32_t k, int32_t stride, int64_t *kmer_off);
+int ssq_kmers64(ssq_ctx *ctx, int in_klass, const uint64_t *words, const int64_t *word_off, const void *lens, int64_t n,
+                int32_t k, int32_t stride, const int64_t *kmer_off, uint64_t *out_words, uint8_t *out_lens);
+/* Opt-in tolerant alphabet: out = ascii with a c g t rewritten to upper case and u U to T (the reference's table_91
+ * maps U to T's code, util.pyx:44-50, but its validators reject U and lower case; the default stays exact A C G T).
+ * Pack `out` with the offsets of `ascii`. */
+int ssq_normalize(ssq_ctx *ctx, const uint8_t *ascii, int64_t nbytes, uint8_t *out);
+
 /* ---- synthetic reads (measurement tooling) ----------------
  * Deterministic counter-based generator, identical to oracle/ssq_oracle.c's
  * ssq_oracle_synth_reads.  offsets[n+1] and ascii are outputs; ascii must hold

@@ -83,6 +83,11 @@ PROTOTYPES = {
     "ssq_host_pack_count": (_int, [_p, _p, _p, _p, _i64, _p, _p, _i64, C.POINTER(Report)]),
     "ssq_host_pack_count_lens": (_int, [_p, _p, _p, _p, _i64, _p, _i64, C.POINTER(Report)]),
     "ssq_synth_reads": (_int, [_p, _u64, _i64, _i64, _i64, _i32, _i32, _p, _p]),
+    "ssq_slice_words": (_int, [_p, _int, _p, _i64, _p, _p, _i64, _i64, _i32, _p]),
+    "ssq_slice": (_int, [_p, _int, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i32, _int, _p, _p, _p]),
+    "ssq_kmers_count": (_int, [_p, _int, _p, _i64, _i32, _i32, _p]),
+    "ssq_kmers64": (_int, [_p, _int, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
+    "ssq_normalize": (_int, [_p, _p, _i64, _p]),
 }
 
 _LIB = None

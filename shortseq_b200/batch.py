@@ -137,11 +137,19 @@ class ShortSeqArray:
             i += n
         if not 0 <= i < n:
             raise IndexError("ShortSeqArray index out of range")
+        length = int(l[i])
         if self.klass == CLASS_64:
-            return _box(CLASS_64, (int(w[i]),), int(l[i]))
-        if self.klass == CLASS_192:
-            return _box(CLASS_192, tuple(int(x) for x in w[i]), int(l[i]))
-        return _box(CLASS_VAR, tuple(int(x) for x in w[wo[i]: wo[i + 1]]), int(l[i]))
+            blocks = (int(w[i]),)
+        elif self.klass == CLASS_192:
+            blocks = tuple(int(x) for x in w[i])
+        else:
+            blocks = tuple(int(x) for x in w[wo[i]: wo[i + 1]])
+        # the object class follows the element's own length (an element of a slice_batch result may be shorter than
+        # its array's class, reference short_seq.pyx:94-116); bits >= 2 len are zero, so dropping / padding blocks is exact
+        k = class_of_length(length)
+        nb = 1 if k == CLASS_64 else (3 if k == CLASS_192 else max(1, (length + 31) // 32))
+        blocks = (blocks + (0,) * nb)[:nb]
+        return _box(k, blocks, length)
 
     def __iter__(self):
         for i in range(len(self)):
@@ -159,6 +167,12 @@ class ShortSeqArray:
 
     def hamming(self, other):
         return hamming_batch(self, other)
+
+    def slice(self, start=0, stop=None):
+        return slice_batch(self, start, stop)
+
+    def kmers(self, k, stride=1):
+        return kmers_batch(self, k, stride)
 
 
 def _alloc_out(ctx, klass, n):
@@ -211,6 +225,75 @@ def pack_batch(source, offsets=None, klass=None, device=None):
     arr, rep = _pack_raw(b, klass)
     raise_for_report(rep, b)
     return arr
+
+
+def normalize_batch(source, offsets=None, device=None):
+    """Opt-in tolerant alphabet: a ReadBatch in which a c g t are upper-cased and u / U read as T.
+    The reference rejects all of these (its table_91 maps U to T's code but the validator refuses it, util.pyx:44-50);
+    pack_batch(normalize_batch(...)) accepts them."""
+    b = ReadBatch.make(source, offsets, device)
+    out = torch.empty_like(b.ascii)
+    _lib.check(_lib.lib().ssq_normalize(b.ctx.bind(), ptr(b.ascii), int(b.ascii.numel()), ptr(out)))
+    return ReadBatch(b.ctx, out, b.offsets)
+
+
+def slice_batch(arr, start=0, stop=None):
+    """arr[i][start:stop] for every read of a ShortSeqArray in one launch (reference short_seq.pyx:94-238, per object).
+
+    start / stop: Python ints with slice semantics (None, negative values), or int64 tensors / arrays with one value per
+    read (non-negative).  The class of the result follows the largest possible slice length, as the reference's result
+    class follows the slice length: <= 32 -> CLASS_64, <= 96 -> CLASS_192, else CLASS_VAR.  Boxing an element of the
+    result (`out[i]`) picks the object class from that element's own length."""
+    ctx, L, n = arr.ctx, _lib.lib(), len(arr)
+    max_len = MAX_NT[arr.klass]
+
+    def per_read(v):
+        return v is not None and not isinstance(v, int)
+
+    starts = stops = None
+    start0, stop0 = 0, max_len
+    if per_read(start) or per_read(stop) or (isinstance(start, int) and start < 0) or (isinstance(stop, int) and stop < 0):
+        lens = arr.lens.to(torch.int64)
+        st = torch.zeros_like(lens) if start is None else (to_device(ctx, start, torch.int64) if per_read(start) else torch.full_like(lens, start))
+        sp = lens.clone() if stop is None else (to_device(ctx, stop, torch.int64) if per_read(stop) else torch.full_like(lens, stop))
+        st = torch.where(st < 0, torch.clamp(st + lens, min=0), st)
+        sp = torch.where(sp < 0, torch.clamp(sp + lens, min=0), sp)
+        starts, stops = st.contiguous(), sp.contiguous()
+        width = int(torch.clamp(torch.minimum(sp, lens) - torch.minimum(st, lens), min=0).max()) if n else 0
+    else:
+        start0 = 0 if start is None else start
+        stop0 = max_len if stop is None else stop
+        width = max(0, min(stop0, max_len) - start0)
+    out_klass = CLASS_64 if width <= 32 else (CLASS_192 if width <= 96 else CLASS_VAR)
+    h = ctx.bind()
+    word_off = None
+    if out_klass == CLASS_VAR:
+        word_off = ctx.empty((n + 1,), torch.int64)
+        _lib.check(L.ssq_slice_words(h, arr.klass, ptr(arr.lens), n, ptr(starts), ptr(stops), start0, stop0, width, ptr(word_off)))
+        words = ctx.empty((int(word_off[-1]) if n else 0,), torch.int64)
+        lens_out = ctx.empty((n,), torch.int16)
+    else:
+        words, lens_out = _alloc_out(ctx, out_klass, n)
+    _lib.check(L.ssq_slice(h, arr.klass, ptr(arr.words), ptr(arr.word_off), ptr(arr.lens), n, ptr(starts), ptr(stops), start0, stop0,
+                           width, out_klass, ptr(words), ptr(word_off), ptr(lens_out)))
+    raise_for_report(ctx.sync())
+    return ShortSeqArray(ctx, out_klass, words, lens_out, word_off)
+
+
+def kmers_batch(arr, k, stride=1):
+    """Every k-mer (k <= 32) of every read -> (ShortSeqArray of CLASS_64 k-mers grouped by read, kmer_off int64 [n+1]).
+    `DeviceCounter(CLASS_64).insert(kmers)` then counts them."""
+    if not 1 <= k <= 32 or stride < 1:
+        raise ValueError("k must be 1..32 and stride >= 1")
+    ctx, L, n = arr.ctx, _lib.lib(), len(arr)
+    h = ctx.bind()
+    kmer_off = ctx.empty((n + 1,), torch.int64)
+    _lib.check(L.ssq_kmers_count(h, arr.klass, ptr(arr.lens), n, k, stride, ptr(kmer_off)))
+    total = int(kmer_off[-1]) if n else 0
+    words, lens = ctx.empty((total,), torch.int64), ctx.empty((total,), torch.uint8)
+    _lib.check(L.ssq_kmers64(h, arr.klass, ptr(arr.words), ptr(arr.word_off), ptr(arr.lens), n, k, stride, ptr(kmer_off), ptr(words), ptr(lens)))
+    raise_for_report(ctx.sync())
+    return ShortSeqArray(ctx, CLASS_64, words, lens), kmer_off
 
 
 def split_by_class(h_ascii, h_off):

@@ -47,6 +47,28 @@ struct SynthLen {
     }
 };
 
+// k-mers of a read: (len - k) / stride + 1 when len >= k (ssq_slice.cu)
+struct KmerCount {
+    const void *lens; int len_bytes; int k, stride;
+    __device__ int64_t operator()(int64_t i) const {
+        const int64_t len = len_bytes == 2 ? ((const uint16_t *)lens)[i] : ((const uint8_t *)lens)[i];
+        return len >= k ? (len - k) / stride + 1 : 0;
+    }
+};
+// 64-bit words of the slice [start, stop) of a read, clamped like ssq_slice does
+struct SliceWords {
+    const void *lens; int len_bytes; const int64_t *starts, *stops; int64_t start0, stop0; int32_t width;
+    __device__ int64_t operator()(int64_t i) const {
+        const int64_t len = len_bytes == 2 ? ((const uint16_t *)lens)[i] : ((const uint8_t *)lens)[i];
+        int64_t a = starts ? starts[i] : start0, b = stops ? stops[i] : stop0;
+        a = a < 0 ? 0 : (a > len ? len : a);
+        b = b > len ? len : b;
+        if (b < a) b = a;
+        if (b - a > width) b = a + width;
+        return (b - a + 31) >> 5;
+    }
+};
+
 __device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *total, int64_t *smem /*[8]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t incl = v;
@@ -167,6 +189,15 @@ int scan_fastq_flags(ssq_ctx *ctx, const int64_t *starts, const int64_t *ends, i
 
 int scan_fastq_lens(ssq_ctx *ctx, const int64_t *starts, const int64_t *ends, const int64_t *sel, int64_t n, int64_t *out) {
     return scan_exclusive(ctx, FastqSelLen{starts, ends, sel}, n, out);
+}
+
+int scan_kmer_counts(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int k, int stride, int64_t *out) {
+    return scan_exclusive(ctx, KmerCount{lens, len_bytes, k, stride}, n, out);
+}
+
+int scan_slice_words(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, const int64_t *starts, const int64_t *stops, int64_t start0,
+                     int64_t stop0, int32_t width, int64_t *out) {
+    return scan_exclusive(ctx, SliceWords{lens, len_bytes, starts, stops, start0, stop0, width}, n, out);
 }
 
 int scan_var_words(ssq_ctx *ctx, const int64_t *offsets, int64_t n, int64_t *word_off) {

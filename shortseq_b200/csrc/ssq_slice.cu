@@ -1,0 +1,228 @@
+// ssq_slice.cu -- batched slicing and k-mer extraction over packed arrays, and the tolerant (U / lower case) alphabet.
+//
+// "Next" row N4 of SURVEY section 8f.  The reference slices one object at a time on the host
+// (short_seq.pyx:94-116 _slice, :119-199 _slice_to_ShortSeq64/192/Var, :202-238 _shift_copy_trim): the blocks of the
+// source are funnel-shifted so that base `start` lands in bits 0..1 of block 0, and the tail is trimmed (bzhi) so that
+// whole-block compares and popcounts of the result stay valid.  Here the same is done for a whole array per launch:
+// a sub-sequence is just the bits [2 start, 2 (start + len)) of the read's packed words.
+//   ssq_slice      out[i] = in[i][start_i : start_i + width]  (Python slice clamping; the output class is chosen by the
+//                  caller from `width`, like the reference's result class follows the slice length)
+//   ssq_kmers64    every k-mer (k <= 32, step `stride`) of every read as ShortSeq64 words, grouped by read (CSR offsets
+//                  from ssq_kmers_count); feeding them to ssq_counter_insert is k-mer counting
+//   ssq_normalize  opt-in alphabet: a c g t u U are rewritten to A C G T T T before packing (the reference's table_91
+//                  maps U to T's code, util.pyx:44-50, but its validator rejects it; lower case is always rejected)
+#include "ssq_internal.h"
+
+namespace ssq {
+
+int scan_kmer_counts(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, int k, int stride, int64_t *out);
+int scan_slice_words(ssq_ctx *ctx, const void *lens, int len_bytes, int64_t n, const int64_t *starts, const int64_t *stops, int64_t start0,
+                     int64_t stop0, int32_t width, int64_t *out);
+
+constexpr int kSliceThreads = 256;
+
+// A packed array of any class as the kernels see it.
+struct PackedView {
+    const u64 *words;
+    const int64_t *word_off;   // ShortSeqVar only
+    const void *lens;          // uint8 (ShortSeq64 / ShortSeq192) or uint16 (ShortSeqVar)
+    int klass;
+};
+
+__device__ __forceinline__ u32 view_len(const PackedView &v, int64_t i) {
+    return v.klass == SSQ_CLASS_VAR ? ((const uint16_t *)v.lens)[i] : ((const uint8_t *)v.lens)[i];
+}
+// first word and number of words of read i
+__device__ __forceinline__ const u64 *view_words(const PackedView &v, int64_t i, u32 len, u32 &nwords) {
+    if (v.klass == SSQ_CLASS_64) { nwords = 1; return v.words + i; }
+    if (v.klass == SSQ_CLASS_192) { nwords = 3; return v.words + 3 * i; }
+    nwords = (len + 31) >> 5;
+    return v.words + v.word_off[i];
+}
+// 64 bits of a read's code stream starting at bit `bit` (even); words past the end read as 0
+__device__ __forceinline__ u64 bits_at(const u64 *w, u32 nwords, u32 bit) {
+    const u32 wi = bit >> 6, sh = bit & 63;
+    const u64 lo = wi < nwords ? w[wi] : 0ull;
+    if (sh == 0) return lo;
+    const u64 hi = wi + 1 < nwords ? w[wi + 1] : 0ull;
+    return (lo >> sh) | (hi << (64 - sh));
+}
+__device__ __forceinline__ u64 keep_low_bits(u64 x, int nbits) {
+    if (nbits >= 64) return x;
+    if (nbits <= 0) return 0;
+    return x & ((1ull << nbits) - 1);
+}
+// [start, stop) clamped to a read of `len` bases (both already non-negative: the caller resolves Python's negative
+// indices) and to at most `width` bases -> first base, number of bases
+__device__ __forceinline__ void clamp_slice(int64_t start, int64_t stop, int32_t width, u32 len, u32 &s, u32 &n) {
+    int64_t a = start < 0 ? 0 : (start > (int64_t)len ? (int64_t)len : start);
+    int64_t b = stop > (int64_t)len ? (int64_t)len : stop;
+    if (b < a) b = a;
+    if (b - a > width) b = a + width;
+    s = (u32)a;
+    n = (u32)(b - a);
+}
+
+// fixed-class output: one thread per read, W_OUT words each
+template <int W_OUT>
+__global__ void __launch_bounds__(kSliceThreads) slice_fixed_kernel(PackedView in, int64_t n, const int64_t *starts, const int64_t *stops, int64_t start0, int64_t stop0, int32_t width,
+                                                                    u64 *out_words, uint8_t *out_lens) {
+    for (int64_t i = (int64_t)blockIdx.x * kSliceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSliceThreads) {
+        const u32 len = view_len(in, i);
+        u32 nwords, s, m;
+        const u64 *w = view_words(in, i, len, nwords);
+        clamp_slice(starts ? starts[i] : start0, stops ? stops[i] : stop0, width, len, s, m);
+#pragma unroll
+        for (int j = 0; j < W_OUT; j++)
+            out_words[i * W_OUT + j] = keep_low_bits(bits_at(w, nwords, 2 * s + 64 * j), 2 * (int)m - 64 * j);
+        out_lens[i] = (uint8_t)m;
+    }
+}
+
+// ShortSeqVar output: one warp per read, lane j owns word j
+__global__ void __launch_bounds__(kSliceThreads) slice_var_kernel(PackedView in, int64_t n, const int64_t *starts, const int64_t *stops, int64_t start0, int64_t stop0, int32_t width,
+                                                                  const int64_t *out_word_off, u64 *out_words, uint16_t *out_lens) {
+    const u32 lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kSliceThreads / 32);
+    for (int64_t i = (int64_t)blockIdx.x * (kSliceThreads / 32) + (threadIdx.x >> 5); i < n; i += warps) {
+        const u32 len = view_len(in, i);
+        u32 nwords, s, m;
+        const u64 *w = view_words(in, i, len, nwords);
+        clamp_slice(starts ? starts[i] : start0, stops ? stops[i] : stop0, width, len, s, m);
+        const u32 ow = (m + 31) >> 5;
+        if (lane < ow) out_words[out_word_off[i] + lane] = keep_low_bits(bits_at(w, nwords, 2 * s + 64 * lane), 2 * (int)m - 64 * (int)lane);
+        if (lane == 0) out_lens[i] = (uint16_t)m;
+    }
+}
+
+// k-mers: one warp per read, lanes write consecutive k-mers
+__global__ void __launch_bounds__(kSliceThreads) kmers64_kernel(PackedView in, int64_t n, int k, int stride, const int64_t *kmer_off,
+                                                                u64 *out_words, uint8_t *out_lens) {
+    const u32 lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kSliceThreads / 32);
+    for (int64_t i = (int64_t)blockIdx.x * (kSliceThreads / 32) + (threadIdx.x >> 5); i < n; i += warps) {
+        const u32 len = view_len(in, i);
+        u32 nwords;
+        const u64 *w = view_words(in, i, len, nwords);
+        const int64_t o = kmer_off[i];
+        const u32 cnt = (u32)(kmer_off[i + 1] - o);
+        for (u32 m = lane; m < cnt; m += 32) {
+            out_words[o + m] = keep_low_bits(bits_at(w, nwords, 2 * m * (u32)stride), 2 * k);
+            out_lens[o + m] = (uint8_t)k;
+        }
+    }
+}
+
+// a c g t u U -> A C G T T T, everything else unchanged (16 bytes per thread; the tail byte by byte)
+__device__ __forceinline__ u32 normalize4(u32 w) {
+    // letters only: bytes whose upper-cased value is in 'A'..'Z' have bit 6 set and bit 7 clear; clearing bit 5 of any
+    // other byte could turn an invalid byte into a valid one ('!' & 0xDF = 0x01 is harmless, but keep the rule simple):
+    // only the ten accepted characters are rewritten, byte by byte through their exact values.
+    u32 out = w;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const u32 c = (w >> (8 * b)) & 0xFFu;
+        u32 r = c;
+        if (c == 'a' || c == 'c' || c == 'g' || c == 't') r = c - 32;
+        else if (c == 'u' || c == 'U') r = 'T';
+        out = (out & ~(0xFFu << (8 * b))) | (r << (8 * b));
+    }
+    return out;
+}
+__global__ void __launch_bounds__(kSliceThreads) normalize_kernel(const uint8_t *in, uint8_t *out, int64_t nbytes) {
+    const int64_t nvec = ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 ? nbytes >> 4 : 0;
+    for (int64_t v = (int64_t)blockIdx.x * kSliceThreads + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kSliceThreads) {
+        uint4 x = reinterpret_cast<const uint4 *>(in)[v];
+        x.x = normalize4(x.x); x.y = normalize4(x.y); x.z = normalize4(x.z); x.w = normalize4(x.w);
+        reinterpret_cast<uint4 *>(out)[v] = x;
+    }
+    for (int64_t i = (nvec << 4) + (int64_t)blockIdx.x * kSliceThreads + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * kSliceThreads) {
+        const u32 c = in[i];
+        out[i] = (uint8_t)(normalize4(c) & 0xFFu);
+    }
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+static int check_view(ssq_ctx *ctx, int klass, const void *words, const void *word_off, const void *lens, int64_t n) {
+    SSQ_ARG(ctx != nullptr, "ctx is NULL");
+    SSQ_ARG(klass == SSQ_CLASS_64 || klass == SSQ_CLASS_192 || klass == SSQ_CLASS_VAR, "bad class");
+    SSQ_ARG(n >= 0, "negative size");
+    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr), "NULL buffer");
+    SSQ_ARG(n == 0 || klass != SSQ_CLASS_VAR || word_off != nullptr, "word_off is NULL");
+    return SSQ_OK;
+}
+
+extern "C" {
+
+int ssq_slice_words(ssq_ctx *ctx, int in_klass, const void *lens, int64_t n, const int64_t *starts, const int64_t *stops,
+                    int64_t start0, int64_t stop0, int32_t width, int64_t *out_word_off) {
+    SSQ_ARG(ctx != nullptr && out_word_off != nullptr && (n == 0 || lens != nullptr) && n >= 0 && width >= 0, "bad arguments");
+    DeviceGuard g(ctx->device);
+    return scan_slice_words(ctx, lens, in_klass == SSQ_CLASS_VAR ? 2 : 1, n, starts, stops, start0, stop0, width, out_word_off);
+}
+
+int ssq_slice(ssq_ctx *ctx, int in_klass, const uint64_t *words, const int64_t *word_off, const void *lens, int64_t n,
+              const int64_t *starts, const int64_t *stops, int64_t start0, int64_t stop0, int32_t width, int out_klass,
+              uint64_t *out_words, const int64_t *out_word_off, void *out_lens) {
+    int rc = check_view(ctx, in_klass, words, word_off, lens, n);
+    if (rc) return rc;
+    SSQ_ARG(width >= 0 && width <= 1024, "width outside 0..1024");
+    SSQ_ARG(out_klass == SSQ_CLASS_64 || out_klass == SSQ_CLASS_192 || out_klass == SSQ_CLASS_VAR, "bad output class");
+    SSQ_ARG(out_klass != SSQ_CLASS_64 || width <= 32, "width > 32 needs ShortSeq192 or ShortSeqVar output");
+    SSQ_ARG(out_klass != SSQ_CLASS_192 || width <= 96, "width > 96 needs ShortSeqVar output");
+    SSQ_ARG(n == 0 || (out_words != nullptr && out_lens != nullptr), "NULL output");
+    SSQ_ARG(n == 0 || out_klass != SSQ_CLASS_VAR || out_word_off != nullptr, "out_word_off is NULL (ssq_slice_words fills it)");
+    if (n == 0) return SSQ_OK;
+    DeviceGuard g(ctx->device);
+    const PackedView in{(const u64 *)words, word_off, lens, in_klass};
+    if (out_klass == SSQ_CLASS_VAR) {
+        const int grid = grid_for(ctx, (n + kSliceThreads / 32 - 1) / (kSliceThreads / 32), 8);
+        slice_var_kernel<<<grid, kSliceThreads, 0, ctx->stream>>>(in, n, starts, stops, start0, stop0, width, out_word_off, (u64 *)out_words,
+                                                                  (uint16_t *)out_lens);
+    } else {
+        const int grid = grid_for(ctx, (n + kSliceThreads - 1) / kSliceThreads, 8);
+        if (out_klass == SSQ_CLASS_64)
+            slice_fixed_kernel<1><<<grid, kSliceThreads, 0, ctx->stream>>>(in, n, starts, stops, start0, stop0, width, (u64 *)out_words, (uint8_t *)out_lens);
+        else
+            slice_fixed_kernel<3><<<grid, kSliceThreads, 0, ctx->stream>>>(in, n, starts, stops, start0, stop0, width, (u64 *)out_words, (uint8_t *)out_lens);
+    }
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_kmers_count(ssq_ctx *ctx, int in_klass, const void *lens, int64_t n, int32_t k, int32_t stride, int64_t *kmer_off) {
+    SSQ_ARG(ctx != nullptr && kmer_off != nullptr && (n == 0 || lens != nullptr) && n >= 0, "bad arguments");
+    SSQ_ARG(k >= 1 && k <= 32 && stride >= 1, "k must be 1..32 and stride >= 1");
+    DeviceGuard g(ctx->device);
+    return scan_kmer_counts(ctx, lens, in_klass == SSQ_CLASS_VAR ? 2 : 1, n, k, stride, kmer_off);
+}
+
+int ssq_kmers64(ssq_ctx *ctx, int in_klass, const uint64_t *words, const int64_t *word_off, const void *lens, int64_t n,
+                int32_t k, int32_t stride, const int64_t *kmer_off, uint64_t *out_words, uint8_t *out_lens) {
+    int rc = check_view(ctx, in_klass, words, word_off, lens, n);
+    if (rc) return rc;
+    SSQ_ARG(k >= 1 && k <= 32 && stride >= 1, "k must be 1..32 and stride >= 1");
+    SSQ_ARG(n == 0 || (kmer_off != nullptr && out_words != nullptr && out_lens != nullptr), "NULL buffer");
+    if (n == 0) return SSQ_OK;
+    DeviceGuard g(ctx->device);
+    const PackedView in{(const u64 *)words, word_off, lens, in_klass};
+    const int grid = grid_for(ctx, (n + kSliceThreads / 32 - 1) / (kSliceThreads / 32), 8);
+    kmers64_kernel<<<grid, kSliceThreads, 0, ctx->stream>>>(in, n, k, stride, kmer_off, (u64 *)out_words, out_lens);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+int ssq_normalize(ssq_ctx *ctx, const uint8_t *ascii, int64_t nbytes, uint8_t *out) {
+    SSQ_ARG(ctx != nullptr && nbytes >= 0 && (nbytes == 0 || (ascii != nullptr && out != nullptr)), "bad arguments");
+    if (nbytes == 0) return SSQ_OK;
+    DeviceGuard g(ctx->device);
+    const int grid = grid_for(ctx, (nbytes / 16 + kSliceThreads) / kSliceThreads, 8);
+    normalize_kernel<<<grid, kSliceThreads, 0, ctx->stream>>>(ascii, out, nbytes);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+}  // extern "C"
