@@ -95,12 +95,32 @@ def words_to_numpy(t):
     return t.detach().cpu().numpy().view(np.uint64)
 
 
+_FASTBOX = False
+
+
+def fastbox():
+    """The CPython helper module (hostext/_fastbox.c: gather / boxing / dict-fill loops in C), or None when it has not
+    been built -- the same loops then run in Python.  Host-side glue only: no sequence arithmetic lives there."""
+    global _FASTBOX
+    if _FASTBOX is False:
+        try:
+            from . import _fastbox as m
+            _FASTBOX = m
+        except ImportError:
+            _FASTBOX = None
+    return _FASTBOX
+
+
 def gather_reads(reads):
     """list of bytes -> (uint8 buffer, int64 offsets[n+1]) on the host.
 
     Mirrors the element check of the reference's `<bytes> PyList_GET_ITEM` cast
     (counter.pyx:27): a non-bytes element is a TypeError.
     """
+    fb = fastbox()
+    if fb is not None and type(reads) is list:
+        buf, off = fb.gather(reads)                     # one C pass for the sizes, one memcpy pass
+        return np.frombuffer(buf, dtype=np.uint8), np.frombuffer(off, dtype=np.int64)
     n = len(reads)
     kinds = set(map(type, reads))                       # C-speed pass; the common case is {bytes}
     if kinds - {bytes}:

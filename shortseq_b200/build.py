@@ -54,7 +54,28 @@ def build(force=False, verbose=False, defines=(), out=None):
     return lib
 
 
+HOSTEXT_SRC = os.path.join(HERE, "hostext", "_fastbox.c")
+
+
+def hostext_path():
+    import sysconfig
+    return os.path.join(HERE, "_fastbox" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_hostext(force=False):
+    """Compile the CPython helper module (gather / boxing loops of the drop-in ShortSeqCounter) with gcc."""
+    import sysconfig
+    out = hostext_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(HOSTEXT_SRC):
+        return out
+    inc = sysconfig.get_paths()["include"]
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-Wall", "-I", inc, HOSTEXT_SRC, "-o", out])
+    return out
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    if not outs:
+        print(build_hostext(force="--force" in sys.argv))

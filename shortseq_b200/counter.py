@@ -173,9 +173,11 @@ class DeviceCounter:
 def count_reads(reads, device=None):
     """Count a list of bytes of mixed lengths on the GPU.
 
-    -> one (klass, words, lens, counts, first_index) tuple of host arrays per length class present.
-    ShortSeqVar-length reads cannot be deduplicated by the reference (its dict hashes the heap
-    pointer, SURVEY trap T3); they are rejected here rather than silently diverging.
+    -> one (klass, words, lens, counts, first_index) tuple of host arrays per length class present.  Reads of 0..96 nt
+    are deduplicated.  ShortSeqVar-length reads (97..1024 nt) come back as one entry PER OCCURRENCE with count 1 and
+    first_index = its list position: that is what the reference's counter does with them (it takes the dict hash from
+    the 8 bytes after the object head, which is the heap pointer of a ShortSeqVar -- counter.pyx:44, short_seq_var.pxd:15
+    -- so equal sequences never meet; SURVEY trap T3).
     """
     h_ascii, h_off = gather_reads(reads)
     lens = np.diff(h_off)
@@ -183,14 +185,19 @@ def count_reads(reads, device=None):
     too_long = np.nonzero(lens > 1024)[0]
     if too_long.size:
         errors.append((int(too_long[0]), Exception(MSG_TOO_LONG)))
-    var = np.nonzero((lens > 96) & (lens <= 1024))[0]
-    if var.size:
-        errors.append((int(var[0]), NotImplementedError(
-            "ShortSeqCounter: reads longer than 96 nt (ShortSeqVar) are not counted -- the reference does not "
-            "deduplicate them either (each occurrence becomes its own key)")))
     groups = []
     for k, idx, sub_ascii, sub_off in _batch.split_by_class(h_ascii, h_off):
         if k == CLASS_VAR:
+            b = _batch.ReadBatch.make(sub_ascii, sub_off, device)
+            arr, rep = _batch._pack_raw(b, CLASS_VAR)
+            if rep.code != _lib.OK:
+                try:
+                    _batch.raise_for_report(rep, b, idx)
+                except Exception as e:  # noqa: BLE001 -- re-raised below in list order
+                    errors.append((int(idx[int(rep.first_bad_read)]), e))
+                continue
+            w, l, wo = arr.to_host()
+            groups.append((CLASS_VAR, (w, wo), l, np.ones(idx.size, dtype=np.int64), idx))
             continue
         ctr = DeviceCounter(k, expected_unique=idx.size, device=device)
         b = _batch.ReadBatch.make(sub_ascii, sub_off, ctr.ctx.device)
@@ -211,19 +218,46 @@ def count_reads(reads, device=None):
     return groups
 
 
-def _fill_in_order(dst, groups):
+def _fill_in_order(dst, groups, add=False):
     """Insert the per-class results (klass, words, lens, counts, first_index arrays) into the dict `dst` in
-    first-occurrence order.  Boxing and the insertion loop run in bulk (dict.update over a zip)."""
-    objs, counts, firsts = [], [], []
+    first-occurrence order.  Boxing and the insertion loop run in C when the helper module is built
+    (hostext/_fastbox.c), else in bulk Python (dict.update over a zip).  ShortSeq64/192 keys are inserted under their
+    hash (the first block); ShortSeqVar keys under their identity, one entry per occurrence, as in the reference."""
+    from ._runtime import fastbox
+    fb = fastbox()
+    objs, counts, firsts, hashes = [], [], [], []
     for klass, w, l, cnt, fi in groups:
-        objs += _box_many(klass, w, l)
-        counts += np.asarray(cnt).tolist()
+        if klass == CLASS_VAR:
+            words, wo = w
+            boxed = [_box(CLASS_VAR, tuple(int(x) for x in words[wo[i]: wo[i + 1]]), int(l[i])) for i in range(len(l))]
+            hs = np.fromiter(map(id, boxed), dtype=np.int64, count=len(boxed))
+        else:
+            wv = np.ascontiguousarray(w).view(np.uint64)
+            if fb is not None:
+                boxed = fb.box_many(ShortSeq64 if klass == CLASS_64 else ShortSeq192, wv.tobytes(),
+                                    np.ascontiguousarray(l, dtype=np.int64).tobytes(), 1 if klass == CLASS_64 else 3)
+            else:
+                boxed = _box_many(klass, w, l)
+            hs = (wv if wv.ndim == 1 else wv[:, 0]).view(np.int64).copy()
+            hs[hs == -1] = -2
+        objs += boxed
+        hashes.append(hs)
+        counts.append(np.asarray(cnt, dtype=np.int64))
         firsts.append(np.asarray(fi, dtype=np.int64))
     if not objs:
         return
-    order = np.argsort(np.concatenate(firsts), kind="stable").tolist()
+    order = np.argsort(np.concatenate(firsts), kind="stable")
+    counts = np.concatenate(counts)
+    if fb is not None:
+        fb.fill_counts(dst, objs, counts.tobytes(), np.concatenate(hashes).tobytes(), order.astype(np.int64).tobytes(), bool(add))
+        return
+    order, counts = order.tolist(), counts.tolist()
     with _NoGC():
-        dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
+        if add:
+            for j in order:
+                dict.__setitem__(dst, objs[j], dict.get(dst, objs[j], 0) + counts[j])
+        else:
+            dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
 
 
 class ShortSeqCounter(dict):
@@ -247,12 +281,7 @@ class ShortSeqCounter(dict):
     def _count_py_bytes_list(self, it):
         if not it:
             return
-        if len(self) == 0:
-            _fill_in_order(self, count_reads(it))
-            return
-        for klass, w, l, cnt, _ in count_reads(it):                 # adding to a non-empty counter
-            for key, count in zip(_box_many(klass, w, l), np.asarray(cnt).tolist()):
-                dict.__setitem__(self, key, dict.get(self, key, 0) + count)
+        _fill_in_order(self, count_reads(it), add=len(self) != 0)   # adding to a non-empty counter sums the counts
 
     @classmethod
     def from_batch(cls, source, offsets=None, klass=None, device=None):

@@ -162,3 +162,26 @@ def test_classify(sq):
     exp = [(lens <= 32).sum(), ((lens > 32) & (lens <= 96)).sum(), ((lens > 96) & (lens <= 1024)).sum(), (lens > 1024).sum(),
            int(np.nonzero(lens > 96)[0][0])]
     assert got.tolist() == [int(x) for x in exp]
+
+
+def test_counter_shortseqvar_keys_like_the_reference(sq):
+    """The reference's counter never deduplicates ShortSeqVar keys: it inserts them under the 8 bytes after the object
+    head, a heap pointer (counter.pyx:44, short_seq_var.pxd:15; SURVEY trap T3).  Same here: one entry per occurrence,
+    count 1, in list order, next to deduplicated ShortSeq64/192 keys."""
+    a, b = b"ACGT" * 40, b"TTGCA" * 30
+    reads = [a, b"ACGT", b, a, b"ACGT", b"G" * 50, a, b"G" * 50]
+    c = sq.ShortSeqCounter(reads)
+    assert [(str(k), v) for k, v in c.items()] == [(a.decode(), 1), ("ACGT", 2), (b.decode(), 1), (a.decode(), 1), ("G" * 50, 2),
+                                                   (a.decode(), 1)]
+    assert [type(k).__name__ for k in c] == ["ShortSeqVar", "ShortSeq64", "ShortSeqVar", "ShortSeqVar", "ShortSeq192", "ShortSeqVar"]
+    from oracle import ref as R
+    ref = R.load()
+    if ref is not None:
+        rc = ref.ShortSeqCounter(reads)
+        assert [(str(k), v) for k, v in rc.items()] == [(str(k), v) for k, v in c.items()]
+    with pytest.raises(Exception, match="longer than 1024"):
+        sq.ShortSeqCounter([b"ACGT", b"A" * 1025])
+    # adding a second list to a non-empty counter sums the counts of the deduplicated classes
+    c2 = sq.ShortSeqCounter([b"ACGT", b"GG"])
+    c2._count_py_bytes_list([b"GG", b"GG", b"T"])
+    assert {str(k): v for k, v in c2.items()} == {"ACGT": 1, "GG": 3, "T": 1}
