@@ -200,7 +200,7 @@ def config_of(args, world):
                     f"({u:.3g} distinct sequences in the generator), BASELINE.json configs[1]",
         "reads_per_gpu": n, "distinct_sequences": u, "read_len": L,
         "parallelism": (f"dp{world}: reads sharded by index, local tables merged by a hash-partitioned exchange of the uniques "
-                        f"({'NCCL all-to-all' if args.nccl_exchange else 'export kernel stores into the owners over NVLink peer memory'})")
+                        f"({'torch.distributed all-to-all-v' if args.nccl_exchange else 'ssq_counter_merge_alltoall: export kernel stores into the owners over NVLink peer memory, device-side arrival flags'})")
         if world > 1 else "single GPU",
         "l2_policy": "inputs (>= 40 GB per step) far exceed the 126 MB L2; no flush needed",
     }
@@ -486,7 +486,10 @@ def cfg_c3(sq, args, peak, world, rank, state):
         pt.step()
         if world > 1:
             pt._lib.check(pt.lib.ssq_counter_clear(owner.handle))
-            merge_alltoall(pt.counter, owner=owner)
+            if state["comm"] is not None:
+                state["comm"].merge(pt.counter, owner)        # ShortSeq192: grouped ncclSend / ncclRecv inside the library
+            else:
+                merge_alltoall(pt.counter, owner=owner)
             return len(owner)
         return len(pt.counter)
 
@@ -517,7 +520,7 @@ def cfg_c3(sq, args, peak, world, rank, state):
     table = owner if world > 1 else pt.counter
     pc = None if args.no_parity else parity_check(sq, table, pt.words, pt.lens, rank * n, n, u, SEED, world, rank, sq.CLASS_192)
     res = {"workload": f"{total:.3g} synthetic 75-nt reads -> ShortSeq192 pack + dedup count, {u:.3g} distinct sequences"
-                       + (f", strong-scaled over {world} GPUs (NCCL all-to-all merge)" if world > 1 else ", 1 GPU"),
+                       + (f", strong-scaled over {world} GPUs (ssq_counter_merge_alltoall)" if world > 1 else ", 1 GPU"),
            "reads_total": total, "reads_per_gpu": n, "ms_per_step": round(ms, 3), "gbases_s": round(total * L / ms / 1e6, 1),
            "pass_ms_rank0": round(pass_ms, 3), "kernel_ms": {"pack+scatter": round(ph[0], 3), "count": round(ph[1] + ph[2], 3)},
            "pass_frac": round(pt.pass_bytes(local_unique) / (pass_ms * 1e-3) / 1e9 / peak, 4),
@@ -709,7 +712,7 @@ def run_ours(args):
     import torch.distributed as dist
     import shortseq_b200 as sq
     from shortseq_b200 import _lib
-    from shortseq_b200.distributed import PeerExchange, PeerExchangeUnavailable, merge_alltoall, merge_peer
+    from shortseq_b200.distributed import Comm, merge_alltoall
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -723,31 +726,26 @@ def run_ours(args):
     # resident inputs: rank r holds reads [r*n, (r+1)*n) of the global generator
     pt = PassTimer(sq, klass, n, u, L, rank=rank)
     ctx, local = pt.ctx, pt.counter
-    owner = exchange = None
+    owner = comm = None
     if world > 1:
         # every rank draws from the same u keys, and owners split the key space evenly by hash
         owner = sq.DeviceCounter(klass, expected_unique=int(1.1 * u / world) + 1024, hash_rot=world.bit_length() - 1)
-        if klass == sq.CLASS_64 and not args.nccl_exchange:
-            exchange = PeerExchange(ctx)
-    state = {"exchange": exchange}
+        if not args.nccl_exchange:
+            comm = Comm(ctx)            # the library's own communicator: NCCL for the sizes, NVLink peer stores for the payload
+    state = {"comm": comm}
     h = ctx.bind()
     uniques_seen = [0]
+    xms = []
 
     def step():
         ev = pt.step()
         if world > 1:
             _lib.check(lib.ssq_counter_clear(owner.handle))
-            if state["exchange"] is not None:
-                try:
-                    merge_peer(local, owner, state["exchange"])   # export kernel stores straight into the owners' memory (NVLink)
-                except PeerExchangeUnavailable as e:              # raised on every rank alike: switch to NCCL for good
-                    if rank == 0:
-                        print(f"bench: {e}; using the NCCL all-to-all exchange", file=sys.stderr, flush=True)
-                    state["exchange"] = None
-                    _lib.check(lib.ssq_counter_clear(owner.handle))
-                    merge_alltoall(local, owner=owner)
+            if comm is not None:
+                comm.merge(local, owner)                  # ssq_counter_merge_alltoall
+                xms.append((comm.exchange_ms, comm.merge_ms))
             else:
-                merge_alltoall(local, owner=owner)        # export, then NCCL all-to-all
+                merge_alltoall(local, owner=owner)        # export, then torch.distributed all-to-all-v
             uniques_seen[0] = len(owner)
         else:
             uniques_seen[0] = len(local)          # device->host read of the step's result
@@ -769,6 +767,7 @@ def run_ours(args):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     del pt.phase_ms[:]
+    del xms[:]
     evs = [step() for _ in range(K)]
     t1.record()
     barrier()
@@ -868,12 +867,16 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "uniques": int(uniques_seen[0]), "table_slots": table_slots, "parity_check": pc, "configs": extra,
         }
+        if world > 1 and xms:
+            line["exchange_ms"] = round(statistics.mean(x[0] for x in xms), 3)      # rank 0: send side (export kernel = peer stores)
+            line["merge_ms"] = round(statistics.mean(x[1] for x in xms), 3)         # rank 0: wait for the senders + owner-side count
+            line["exchange"] = "peer stores over NVLink (ssq_counter_merge_alltoall)" if comm.peer_stores else "grouped ncclSend/ncclRecv (ssq_counter_merge_alltoall)"
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
-        if state["exchange"] is not None:
-            state["exchange"].close()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
 
 
@@ -885,7 +888,7 @@ def run_e2e(sq, args, world, rank, state, barrier, h):
     import torch
     import torch.distributed as dist
     from shortseq_b200 import _lib
-    from shortseq_b200.distributed import merge_alltoall, merge_peer
+    from shortseq_b200.distributed import merge_alltoall
     lib = _lib.lib()
     n, u, L = int(args.reads), int(args.uniques), args.read_len
     klass = sq.CLASS_64 if L <= 32 else sq.CLASS_192
@@ -920,8 +923,8 @@ def run_e2e(sq, args, world, rank, state, barrier, h):
         table = ectr
         if world > 1:
             _lib.check(lib.ssq_counter_clear(eowner.handle))
-            if state["exchange"] is not None:
-                merge_peer(ectr, eowner, state["exchange"])
+            if state["comm"] is not None:
+                state["comm"].merge(ectr, eowner)
             else:
                 merge_alltoall(ectr, owner=eowner)
             table = eowner

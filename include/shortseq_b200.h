@@ -53,6 +53,7 @@ extern "C" {
 #define SSQ_ERR_LEN_MISMATCH 5  /* "Hamming distance requires sequences of equal length" (short_seq_64.pyx:78-80) */
 #define SSQ_ERR_TABLE_FULL 6    /* counter overflowed beyond recovery; the counter must be discarded */
 #define SSQ_ERR_ARG 7           /* invalid argument */
+#define SSQ_ERR_EXCHANGE 8      /* multi-GPU merge: another rank's share never arrived (ssq_counter_merge_alltoall) */
 
 /* container classes (short_seq.pyx:54-74) */
 #define SSQ_CLASS_64 0   /* 0..32 nt   */
@@ -226,6 +227,25 @@ int ssq_counter_export_region_bases(ssq_counter *c, int n_parts, int64_t *const 
 int ssq_counter_export_counts(ssq_counter *c, int n_parts, int64_t *part_counts);
 int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t *const *dst_words,
                           uint8_t *const *dst_lens, uint64_t *const *dst_counts);
+/* ---- multi-GPU merge (the reference is single-process) -----------------------------------------
+ * One process per GPU of one box.  Every rank counts its own shard of the reads into a LOCAL counter (no
+ * communication); ssq_counter_merge_alltoall then moves the distinct keys -- not the reads -- to their OWNER rank
+ * (top log2(world) bits of the key hash) and adds them into `owner` (a counter created with hash_rot = log2(world));
+ * the global counter is the disjoint union of the owner tables.  world must be a power of two.
+ *   ssq_comm_unique_id   rank 0 produces 128 opaque bytes (an ncclUniqueId) and passes them to the others out of band
+ *   ssq_comm_init        collective; NCCL (libnccl.so.2) is loaded at run time
+ *   ssq_counter_merge_alltoall   collective.  ShortSeq64: sizes by ncclAllGather, then the export kernel stores every
+ *       owner's share into that owner's receive buffer over NVLink (CUDA IPC), arrival flags on the device, the owner
+ *       counts region by region in shared memory.  ShortSeq192 / no IPC: grouped ncclSend / ncclRecv of a staged
+ *       export.  exchange_ms / merge_ms (may be NULL): device time of this rank's send side and of its owner-side merge.
+ *   A rank whose peers never deliver gets SSQ_ERR_EXCHANGE from the next ssq_ctx_sync (bounded device-side wait). */
+typedef struct ssq_comm ssq_comm;
+int ssq_comm_unique_id(uint8_t *id128);
+int ssq_comm_init(ssq_ctx *ctx, const uint8_t *id128, int rank, int world, ssq_comm **out);
+int ssq_comm_destroy(ssq_comm *comm);
+int ssq_comm_uses_peer_stores(ssq_comm *comm);
+int ssq_counter_merge_alltoall(ssq_comm *comm, ssq_counter *local, ssq_counter *owner, float *exchange_ms, float *merge_ms);
+
 /* CUDA IPC for the peer exchange: handle64 = 64 opaque bytes to pass to the other single-GPU processes of the box. */
 int ssq_ipc_get_handle(ssq_ctx *ctx, void *dptr, void *handle64);
 int ssq_ipc_open(ssq_ctx *ctx, const void *handle64, void **dptr);

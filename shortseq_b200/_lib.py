@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSQ_LIB") or os.path.join(HERE, "libshortseq_b200.so")
 
-OK, ERR_BAD_BASE, ERR_TOO_LONG, ERR_CLASS, ERR_CUDA, ERR_LEN_MISMATCH, ERR_TABLE_FULL, ERR_ARG = range(8)
+OK, ERR_BAD_BASE, ERR_TOO_LONG, ERR_CLASS, ERR_CUDA, ERR_LEN_MISMATCH, ERR_TABLE_FULL, ERR_ARG, ERR_EXCHANGE = range(9)
 CLASS_64, CLASS_192, CLASS_VAR = 0, 1, 2
 
 
@@ -88,6 +88,11 @@ PROTOTYPES = {
     "ssq_kmers_count": (_int, [_p, _int, _p, _i64, _i32, _i32, _p]),
     "ssq_kmers64": (_int, [_p, _int, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "ssq_normalize": (_int, [_p, _p, _i64, _p]),
+    "ssq_comm_unique_id": (_int, [_p]),
+    "ssq_comm_init": (_int, [_p, _p, _int, _int, C.POINTER(_p)]),
+    "ssq_comm_destroy": (_int, [_p]),
+    "ssq_comm_uses_peer_stores": (_int, [_p]),
+    "ssq_counter_merge_alltoall": (_int, [_p, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
 _LIB = None

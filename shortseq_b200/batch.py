@@ -91,6 +91,8 @@ def raise_for_report(rep, batch=None, index_map=None):
         raise Exception(f"Hamming distance requires sequences of equal length (pair {where})")
     if rep.code == _lib.ERR_TABLE_FULL:
         raise _lib.LibraryError("counter table overflow")
+    if rep.code == _lib.ERR_EXCHANGE:
+        raise _lib.LibraryError("multi-GPU merge: another rank's share never arrived")
     raise _lib.LibraryError(f"device reported status {rep.code}")
 
 

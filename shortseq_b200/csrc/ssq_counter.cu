@@ -33,6 +33,9 @@ int launch_pack_count(ssq_ctx *ctx, int klass, bool scatter, const uint8_t *asci
 constexpr int kThreads = 256;
 
 static TableView view_of(const ssq_counter *c);
+int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *block_counts,
+                               const int64_t *block_regions, int n_blocks, const int64_t *region_bases, int64_t rb_stride,
+                               const u64 *flags, u64 epoch);
 
 // gate[0] = stop flag, gate[1] = index of the first stopped sub-batch
 __global__ void gate_kernel(u64 *gate, const u64 *size, u64 incoming, u64 limit, u64 batch_index) {
@@ -95,10 +98,34 @@ struct MergeRegions {
     int64_t rb_stride;                     // int64 entries between the region_bases of consecutive blocks
 };
 
+// Multi-GPU merge: flags[b] (this GPU's memory) is set to the merge's epoch by sender b once its block has landed
+// (st.release.sys behind its export kernel, ssq_comm.cu).  Bounded spin: a sender that never shows up surfaces as
+// DevReport::exchange_timeout instead of a hung GPU.  Returns false on a timeout.
+__device__ __forceinline__ bool wait_arrival(const u64 *flag, u64 epoch, DevReport *rep) {
+    u64 v = 0;
+    for (u64 it = 0;; ++it) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= epoch) return true;
+        if (it > (1ull << 24)) { atomicAdd(&rep->exchange_timeout, 1ull); return false; }
+        __nanosleep(200);
+    }
+}
+__global__ void wait_flags_kernel(const u64 *flags, int n, u64 epoch, DevReport *rep) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < n) wait_arrival(flags + threadIdx.x, epoch, rep);
+}
+
 __global__ void __launch_bounds__(kThreads, 3) merge_regions_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
-                                                                    const int64_t *region_bases, MergeRegions mr) {
+                                                                    const int64_t *region_bases, MergeRegions mr, const u64 *flags, u64 epoch) {
     extern __shared__ __align__(16) u64 dyn_region[];
     __shared__ u32 s_new[kThreads / 32];
+    __shared__ int s_arrived;
+    if (flags != nullptr) {                                   // every sender's block must have landed before anything is read
+        if (threadIdx.x == 0) s_arrived = 1;
+        __syncthreads();
+        if ((int)threadIdx.x < mr.n && !wait_arrival(flags + threadIdx.x, epoch, t.rep)) s_arrived = 0;
+        __syncthreads();
+        if (!s_arrived) return;
+    }
     const u32 R = 1u << t.log2_region, rmask = R - 1;
     u64 *ks = dyn_region, *cs = dyn_region + R;
     const u32 region = blockIdx.x;
@@ -1236,10 +1263,10 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     return SSQ_OK;
 }
 
-// Regions of up to 2^13 slots (128 KB) are counted in shared memory.
+// Regions of up to 2^14 slots (192 KB of keys + count deltas: one CTA per SM) are counted in shared memory.
 static bool regions_fit_smem(const ssq_counter *c) {
     const int lr = region_bits_for(c->log2_cap);
-    return c->log2_cap >= 22 && lr <= 13;       // >= 2^22 slots: at most 64 level-2 partitions per region
+    return c->log2_cap >= 22 && lr <= 14;       // >= 2^22 slots: at most 64 level-2 partitions per region
 }
 
 static int region_slices() {
@@ -1320,7 +1347,7 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     if (ev_mid) SSQ_CUDA(cudaEventRecord(ev_mid, ctx->stream));
     const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
     const unsigned nseg = rp.slices << (8 - rp.qbits);
-    const int cthreads = env_int("SSQ_COUNT_THREADS", 384, 256, 512);
+    const int cthreads = env_int("SSQ_COUNT_THREADS", t.log2_region >= 14 ? 512 : 384, 256, 512);   // one CTA per SM at 2^14-slot regions: make it a big one
     if (env_int("SSQ_COUNT_V2", 1, 0, 1)) {
         if (cthreads == 256) {
             const size_t bytes = count_regions2_smem<256>(t.log2_region, nseg);
@@ -1398,6 +1425,14 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
             return launch_pack_count(ctx, c->klass, false, ascii, lo, hi, offsets + p, cnt, index_base + p,
                                      words + (size_t)p * W, lens + p, view_of(c), PartView{}, stop);
         });
+    }
+    // A table small enough for L2 takes direct inserts, but at ~1 read per 24 ps the L2 atomic units are the limit
+    // (1e9 reads into 2^21 slots: 23.8 ms against 20 ms for the deferred path): a pass this large gets at least the
+    // smallest table the deferred path works with.
+    if (c->klass == SSQ_CLASS_64 && n >= ((int64_t)1 << 27) && c->log2_cap < 22) {
+        SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        rc = grow(c, 22);
+        if (rc) return rc;
     }
     SSQ_CUDA(cudaEventRecord(c->ev[0], ctx->stream));
     if (use_deferred(c, n)) {
@@ -1580,41 +1615,8 @@ int ssq_counter_regions(ssq_counter *c, int64_t *n_regions) {
 int ssq_counter_merge_regions(ssq_counter *c, const uint64_t *words, const uint8_t *lens, const uint64_t *counts,
                               const int64_t *block_counts, const int64_t *block_regions, int n_blocks,
                               const int64_t *region_bases, int64_t rb_stride) {
-    SSQ_ARG(c != nullptr && block_counts != nullptr && block_regions != nullptr && n_blocks >= 1, "bad arguments");
-    int64_t n = 0;
-    for (int b = 0; b < n_blocks; b++) { SSQ_ARG(block_counts[b] >= 0, "negative block size"); n += block_counts[b]; }
-    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr && region_bases != nullptr), "NULL buffer");
-    if (n == 0) return SSQ_OK;
-    const int lr = region_bits_for(c->log2_cap);
-    const int64_t my_regions = (int64_t)1 << (c->log2_cap - lr);
-    bool ok = c->klass == SSQ_CLASS_64 && c->expected_unique > 0 && n_blocks <= kMaxMergeBlocks && lr <= 12;
-    MergeRegions mr;
-    mr.n = n_blocks;
-    mr.rb_stride = rb_stride;
-    mr.off[0] = 0;
-    for (int b = 0; b < n_blocks && ok; b++) {
-        mr.off[b + 1] = mr.off[b] + block_counts[b];
-        int r = 0;
-        while (((int64_t)my_regions << r) < block_regions[b]) r++;
-        ok = ((int64_t)my_regions << r) == block_regions[b] && block_regions[b] + 1 <= rb_stride;   // a whole number of sender regions per owner region
-        mr.ratio_log2[b] = r;
-    }
-    if (!ok) return insert_common(c, words, lens, counts, n);     // the region grids do not nest: plain weighted insert
-    ssq_ctx *ctx = c->ctx;
-    DeviceGuard g(ctx->device);
-    {
-        const int before = c->log2_cap;
-        int rc0 = make_room(c, n);
-        if (rc0) return rc0;
-        if (c->log2_cap != before || c->expected_unique <= 0) return insert_common(c, words, lens, counts, n);   // the region grid changed under the blocks / bound given up
-    }
-    const size_t bytes = (size_t)16 << lr;
-    int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
-    if (rc) return rc;
-    merge_regions_kernel<<<(unsigned)my_regions, kThreads, bytes, ctx->stream>>>(view_of(c), (const u64 *)words, lens, (const u64 *)counts,
-                                                                              region_bases, mr);
-    SSQ_LAUNCH_CHECK();
-    return finish_pass(c);
+    return counter_merge_regions_impl(c, (const u64 *)words, lens, (const u64 *)counts, block_counts, block_regions, n_blocks, region_bases,
+                                      rb_stride, nullptr, 0);
 }
 
 int ssq_counter_export_region_bases(ssq_counter *c, int n_parts, int64_t *const *dst) {
@@ -1806,3 +1808,56 @@ int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t 
 }
 
 }  // extern "C"
+
+namespace ssq {
+
+// ssq_counter_merge_regions; flags != nullptr (ssq_comm.cu): the blocks are being written by other GPUs and block b is
+// complete once flags[b] >= epoch -- the kernels wait on the device.
+int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *block_counts,
+                               const int64_t *block_regions, int n_blocks, const int64_t *region_bases, int64_t rb_stride,
+                               const u64 *flags, u64 epoch) {
+    SSQ_ARG(c != nullptr && block_counts != nullptr && block_regions != nullptr && n_blocks >= 1, "bad arguments");
+    int64_t n = 0;
+    for (int b = 0; b < n_blocks; b++) { SSQ_ARG(block_counts[b] >= 0, "negative block size"); n += block_counts[b]; }
+    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr && region_bases != nullptr), "NULL buffer");
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    auto plain = [&]() -> int {                              // weighted global insert of everything received
+        if (flags) {
+            wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(flags, n_blocks, epoch, ctx->d_report);
+            SSQ_LAUNCH_CHECK();
+        }
+        if (n == 0) return SSQ_OK;
+        return ::insert_common(c, (const uint64_t *)words, lens, (const uint64_t *)counts, n);
+    };
+    if (n == 0) return plain();
+    const int lr = region_bits_for(c->log2_cap);
+    const int64_t my_regions = (int64_t)1 << (c->log2_cap - lr);
+    bool ok = c->klass == SSQ_CLASS_64 && c->expected_unique > 0 && n_blocks <= kMaxMergeBlocks && lr <= 12;
+    MergeRegions mr;
+    mr.n = n_blocks;
+    mr.rb_stride = rb_stride;
+    mr.off[0] = 0;
+    for (int b = 0; b < n_blocks && ok; b++) {
+        mr.off[b + 1] = mr.off[b] + block_counts[b];
+        int r = 0;
+        while (((int64_t)my_regions << r) < block_regions[b]) r++;
+        ok = ((int64_t)my_regions << r) == block_regions[b] && block_regions[b] + 1 <= rb_stride;   // a whole number of sender regions per owner region
+        mr.ratio_log2[b] = r;
+    }
+    if (!ok) return plain();                                 // the region grids do not nest: plain weighted insert
+    {
+        const int before = c->log2_cap;
+        int rc0 = make_room(c, n);
+        if (rc0) return rc0;
+        if (c->log2_cap != before || c->expected_unique <= 0) return plain();   // the region grid changed under the blocks / bound given up
+    }
+    const size_t bytes = (size_t)16 << lr;
+    int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
+    if (rc) return rc;
+    merge_regions_kernel<<<(unsigned)my_regions, kThreads, bytes, ctx->stream>>>(view_of(c), words, lens, counts, region_bases, mr, flags, epoch);
+    SSQ_LAUNCH_CHECK();
+    return finish_pass(c);
+}
+
+}  // namespace ssq

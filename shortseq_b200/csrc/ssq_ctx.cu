@@ -151,6 +151,11 @@ int ssq_ctx_sync(ssq_ctx *ctx, ssq_report *report) {
     if (r.first_bad_base < best) { best = r.first_bad_base; code = SSQ_ERR_BAD_BASE; }
     if (r.first_len_mismatch < best) { best = r.first_len_mismatch; code = SSQ_ERR_LEN_MISMATCH; }
     if (code == SSQ_OK && r.table_overflow != 0) { code = SSQ_ERR_TABLE_FULL; best = kNoIndex; }
+    if (r.exchange_timeout != 0) {          // a peer's arrival flag never showed up: the merged counts are incomplete
+        set_error("multi-GPU merge: %llu arrival flag(s) of other ranks did not show up in time", (unsigned long long)r.exchange_timeout);
+        code = SSQ_ERR_EXCHANGE;
+        best = kNoIndex;
+    }
     if (report) {
         report->code = code;
         report->first_bad_read = best == kNoIndex ? -1 : (int64_t)best;

@@ -18,7 +18,8 @@ struct DevReport {
     u64 first_too_long;      // lowest read index longer than 1024
     u64 first_len_mismatch;  // lowest pair index with len_a != len_b (Hamming)
     u64 table_overflow;      // number of inserts that found no slot (counter unusable if != 0)
-    u64 pad[3];
+    u64 exchange_timeout;    // multi-GPU merge: arrival flags that never showed up (ssq_comm.cu)
+    u64 pad[2];
 };
 
 // ---- hashing ---------------------------------------------------------------

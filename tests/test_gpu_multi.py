@@ -18,7 +18,7 @@ def _free_port():
 def _worker(rank, world, port, klass, out_dir, peer=False):
     import torch.distributed as dist
     import shortseq_b200 as sq
-    from shortseq_b200.distributed import PeerExchange, global_size, merge_alltoall, merge_peer
+    from shortseq_b200.distributed import Comm, global_size, merge_alltoall
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -28,12 +28,13 @@ def _worker(rank, world, port, klass, out_dir, peer=False):
         local = sq.DeviceCounter(klass, expected_unique=50_000)
         local.pack_count(b)
         if peer:
-            ex = PeerExchange(local.ctx)
+            comm = Comm(local.ctx)
             owner = sq.DeviceCounter(klass, expected_unique=40_000, hash_rot=world.bit_length() - 1)
-            for _ in range(2):                      # twice: buffers are reused, the owner table is cleared in between
+            for _ in range(3):                      # repeatedly: buffers and arrival flags are reused, the owner table is cleared in between
                 owner.clear()
-                merge_peer(local, owner, ex)
-            ex.close()
+                comm.merge(local, owner)
+            assert comm.peer_stores or klass == 1 or os.environ.get("SSQ_NO_PEER_EXCHANGE")
+            comm.close()
         else:
             owner = merge_alltoall(local)
         total = global_size(owner)
@@ -44,9 +45,11 @@ def _worker(rank, world, port, klass, out_dir, peer=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("klass,peer", [(0, False), (1, False), (0, True)])
+@pytest.mark.parametrize("klass,peer", [(0, False), (1, False), (0, True), (1, True)])
 def test_multi_gpu_merge_matches_oracle(tmp_path, klass, peer, oracle):
-    """peer=True: the export kernel stores each owner's tuples straight into that owner's memory (CUDA IPC + NVLink)."""
+    """peer=True: ssq_counter_merge_alltoall inside the C library -- ShortSeq64: the export kernel stores each owner's tuples
+    straight into that owner's memory (CUDA IPC + NVLink) and the owner waits for device-side arrival flags; ShortSeq192:
+    grouped ncclSend / ncclRecv.  peer=False: the torch.distributed spelling of the same exchange."""
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
