@@ -206,7 +206,7 @@ def config_of(args, world):
     }
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -220,7 +220,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -694,7 +694,7 @@ def cfg_c1(sq, c1_cpu):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, emit):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -873,7 +873,7 @@ def run_ours(args):
             line["exchange"] = "peer stores over NVLink (ssq_counter_merge_alltoall)" if comm.peer_stores else "grouped ncclSend/ncclRecv (ssq_counter_merge_alltoall)"
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         if comm is not None:
             comm.close()
@@ -963,10 +963,21 @@ def run_e2e(sq, args, world, rank, state, barrier, h):
 
 def main():
     args = parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one): everything
+    # written to file descriptor 1 while the bench runs goes to stderr, and only the final line to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+
+    def emit(line):
+        out.write(json.dumps(line) + "\n")
+        out.flush()
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
     else:
-        run_ours(args)
+        run_ours(args, emit)
 
 
 if __name__ == "__main__":
