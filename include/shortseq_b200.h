@@ -310,6 +310,18 @@ int ssq_kmers64(ssq_ctx *ctx, int in_klass, const uint64_t *words, const int64_t
  * Pack `out` with the offsets of `ascii`. */
 int ssq_normalize(ssq_ctx *ctx, const uint8_t *ascii, int64_t nbytes, uint8_t *out);
 
+/* ---- UMI collapse ------------------------------------------------------------------------
+ * Clusters the distinct UMIs (ShortSeq64 words / lens with their counts, e.g. a counter's export) of every group
+ * [group_off[g], group_off[g+1]) by Hamming distance, with UMI-tools' published rules (network.py; the reference itself
+ * only compares `a ^ b` with UMI-tools' edit_distance, README.md:82-88, and sketches packed UMI objects,
+ * shortseq/umi/umi.pxd:31-55).  method 0 "directional": a claims b when hamming(a, b) <= threshold and
+ * count[a] >= 2 count[b] - 1, UMIs visited by decreasing count (ties: input order); method 1 "cluster": connected
+ * components of hamming <= threshold.  UMIs of different lengths are never adjacent.
+ * rep[i] = index (into the input arrays) of the representative of UMI i; n_clusters[g] (may be NULL) = clusters of group g. */
+int ssq_umi_cluster(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, const uint64_t *counts, int64_t n,
+                    const int64_t *group_off, int64_t n_groups, int32_t threshold, int32_t method, int64_t *rep,
+                    int64_t *n_clusters);
+
 /* ---- synthetic reads (measurement tooling) ----------------
  * Deterministic counter-based generator, identical to oracle/ssq_oracle.c's
  * ssq_oracle_synth_reads.  offsets[n+1] and ascii are outputs; ascii must hold

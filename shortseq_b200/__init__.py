@@ -15,7 +15,7 @@ from ._runtime import ShortSeqClassError
 from .short_seq import (ShortSeq64, ShortSeq192, ShortSeqVar, pack, from_str, from_bytes, empty, decode_many, hamming_many,
                         get_domain_64, get_domain_192, get_domain_var)
 from .batch import (ReadBatch, ShortSeqArray, pack_batch, pack_mixed, decode_batch, hamming_batch, hamming_refset,
-                    synth_reads, slice_batch, kmers_batch, normalize_batch)
+                    synth_reads, slice_batch, kmers_batch, normalize_batch, umi_collapse)
 from .counter import DeviceCounter, ShortSeqCounter, read_and_count_fastq
 
 MIN_VAR_NT, MAX_VAR_NT = get_domain_var()
@@ -28,5 +28,5 @@ __all__ = [
     "MIN_64_NT", "MAX_64_NT", "MIN_192_NT", "MAX_192_NT", "MIN_VAR_NT", "MAX_VAR_NT",
     "pack_batch", "pack_mixed", "decode_batch", "hamming_batch", "hamming_refset", "synth_reads",
     "ReadBatch", "ShortSeqArray", "DeviceCounter", "CLASS_64", "CLASS_192", "CLASS_VAR",
-    "LibraryError", "ShortSeqClassError", "empty", "decode_many", "hamming_many", "slice_batch", "kmers_batch", "normalize_batch",
+    "LibraryError", "ShortSeqClassError", "empty", "decode_many", "hamming_many", "slice_batch", "kmers_batch", "normalize_batch", "umi_collapse",
 ]

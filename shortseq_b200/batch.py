@@ -298,6 +298,32 @@ def kmers_batch(arr, k, stride=1):
     return ShortSeqArray(ctx, CLASS_64, words, lens), kmer_off
 
 
+def umi_collapse(umis, counts, group_off=None, threshold=1, method="directional"):
+    """Cluster distinct UMIs by Hamming distance with UMI-tools' rules (README.md:82-88 of the reference).
+
+    umis: ShortSeqArray of CLASS_64 (distinct UMIs, e.g. the keys of DeviceCounter.export); counts: their multiplicities
+    (int64 tensor / array); group_off: int64 [g + 1] boundaries of independent groups (None: one group).
+    method "directional" (count[a] >= 2 count[b] - 1 along every edge) or "cluster" (connected components).
+    -> (rep int64 tensor [n]: index of every UMI's representative, cluster_counts int64 tensor [n]: summed counts at the
+    representatives and 0 elsewhere, n_clusters int64 tensor [g])."""
+    if umis.klass != CLASS_64:
+        raise TypeError("umi_collapse needs a ShortSeq64 array (UMIs are at most 32 nt)")
+    ctx, n = umis.ctx, len(umis)
+    cnt = to_device(ctx, counts, torch.int64)
+    if cnt.numel() != n:
+        raise ValueError("counts and umis differ in size")
+    goff = torch.tensor([0, n], dtype=torch.int64, device=ctx.device) if group_off is None else to_device(ctx, group_off, torch.int64)
+    g = int(goff.numel()) - 1
+    rep = ctx.empty((n,), torch.int64)
+    ncl = ctx.empty((g,), torch.int64)
+    m = {"directional": 0, "cluster": 1}[method]
+    _lib.check(_lib.lib().ssq_umi_cluster(ctx.bind(), ptr(umis.words), ptr(umis.lens), ptr(cnt), n, ptr(goff), g, int(threshold), m,
+                                          ptr(rep), ptr(ncl)))
+    raise_for_report(ctx.sync())
+    cluster_counts = torch.zeros_like(cnt).index_add_(0, rep, cnt)
+    return rep, cluster_counts, ncl
+
+
 def split_by_class(h_ascii, h_off):
     """Host-side split of a mixed batch into per-class sub-batches.
 

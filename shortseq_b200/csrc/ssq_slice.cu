@@ -226,3 +226,124 @@ int ssq_normalize(ssq_ctx *ctx, const uint8_t *ascii, int64_t nbytes, uint8_t *o
 }
 
 }  // extern "C"
+
+namespace ssq {
+
+// ---- UMI collapse ---------------------------------------------------------------------------
+// The consumer of config C5's Hamming kernel: within every group of distinct UMIs (one group per mapping position, say),
+// find the UMIs within `threshold` mismatches of each other and merge them into clusters, UMI-tools style.  The
+// reference only has an unfinished sketch of packed UMI objects (shortseq/umi/umi.pxd:31-55) and its README measures
+// `a ^ b` against UMI-tools' edit_distance (README.md:82-88, tests/benchmark.py:125-165); the clustering rules are the
+// published ones of UMI-tools (network.py):
+//   directional   edge a -> b when hamming(a, b) <= threshold and count[a] >= 2 count[b] - 1; UMIs are visited in order of
+//                 decreasing count (ties: input order) and every unvisited UMI claims all it can reach.  The
+//                 representative of a UMI is therefore the best-ranked UMI it is reachable from, which is what the kernel
+//                 computes: labels start as ranks and the minimum flows along the edges until nothing changes.
+//   cluster       the same with undirected edges hamming(a, b) <= threshold: connected components, represented by their
+//                 most frequent member.
+// One CTA per group; all-pairs distances are recomputed in every sweep (xor + popc per pair, the C5 arithmetic) instead of
+// storing an n x n adjacency.  Groups of up to 4096 UMIs are staged in shared memory; larger ones work out of global
+// scratch.
+constexpr int kUmiThreads = 256;
+constexpr int kUmiSmemGroup = 4096;
+struct UmiScratch { u32 *label, *by_rank; };
+
+__global__ void __launch_bounds__(kUmiThreads) umi_cluster_kernel(const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *group_off,
+                                                                  int64_t n_groups, int threshold, int method, int64_t *rep, int64_t *n_clusters,
+                                                                  UmiScratch sc) {
+    extern __shared__ __align__(16) u64 umi_smem[];
+    __shared__ int s_changed;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t base = group_off[g];
+        const u32 n = (u32)(group_off[g + 1] - base);
+        if (n == 0) { if (threadIdx.x == 0 && n_clusters) n_clusters[g] = 0; continue; }
+        const bool staged = n <= (u32)kUmiSmemGroup;
+        // word (8) | count (8) | len (1, padded) | label (4) | by_rank (4)
+        const u64 *w = words + base;
+        const u64 *c = counts + base;
+        const uint8_t *l = lens + base;
+        u32 *label = sc.label + base, *by_rank = sc.by_rank + base;
+        if (staged) {
+            u64 *sw = umi_smem, *scn = umi_smem + n;
+            u32 *sl = reinterpret_cast<u32 *>(umi_smem + 2 * (size_t)n);
+            uint8_t *sll = reinterpret_cast<uint8_t *>(sl + 2 * (size_t)n);
+            for (u32 i = threadIdx.x; i < n; i += kUmiThreads) { sw[i] = w[i]; scn[i] = c[i]; sll[i] = l[i]; }
+            w = sw; c = scn; l = sll; label = sl; by_rank = sl + n;
+        }
+        __syncthreads();
+        // rank: decreasing count, ties in input order
+        for (u32 v = threadIdx.x; v < n; v += kUmiThreads) {
+            const u64 cv = c[v];
+            u32 r = 0;
+            for (u32 u = 0; u < n; u++) r += (c[u] > cv || (c[u] == cv && u < v)) ? 1u : 0u;
+            label[v] = r;
+            by_rank[r] = v;
+        }
+        __syncthreads();
+        // the minimum label flows along the edges until a sweep changes nothing
+        for (;;) {
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            for (u32 v = threadIdx.x; v < n; v += kUmiThreads) {
+                const u64 wv = w[v], cv = c[v];
+                const u32 lv = l[v];
+                u32 best = label[v];
+                for (u32 u = 0; u < n; u++) {
+                    const u32 lu = label[u];
+                    if (lu >= best || l[u] != lv) continue;
+                    if (method == 0 && c[u] + 1 < 2 * cv) continue;          // directional: count[u] >= 2 count[v] - 1
+                    if (diff_bases(w[u], wv) <= threshold) best = lu;
+                }
+                if (best < label[v]) { label[v] = best; s_changed = 1; }       // labels only decrease: a stale read costs a sweep, not correctness
+            }
+            __syncthreads();
+            const int again = s_changed;
+            __syncthreads();
+            if (!again) break;
+        }
+        u32 mine = 0;
+        for (u32 v = threadIdx.x; v < n; v += kUmiThreads) {
+            rep[base + v] = base + by_rank[label[v]];
+            mine += by_rank[label[v]] == v ? 1u : 0u;             // v represents itself: one cluster
+        }
+        if (n_clusters) {
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            if (mine) atomicAdd(&s_changed, (int)mine);
+            __syncthreads();
+            if (threadIdx.x == 0) n_clusters[g] = s_changed;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ssq
+
+extern "C" {
+
+int ssq_umi_cluster(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, const uint64_t *counts, int64_t n,
+                    const int64_t *group_off, int64_t n_groups, int32_t threshold, int32_t method, int64_t *rep,
+                    int64_t *n_clusters) {
+    SSQ_ARG(ctx != nullptr && n >= 0 && n_groups >= 0, "bad arguments");
+    SSQ_ARG(n == 0 || (words != nullptr && lens != nullptr && counts != nullptr && group_off != nullptr && rep != nullptr), "NULL buffer");
+    SSQ_ARG(threshold >= 0 && threshold <= 32 && (method == 0 || method == 1), "threshold must be 0..32, method 0 (directional) or 1 (cluster)");
+    if (n == 0 || n_groups == 0) return SSQ_OK;
+    ssq::DeviceGuard g(ctx->device);
+    void *scratch = nullptr;
+    int rc = ssq::ctx_scratch(ctx, sizeof(ssq::u32) * 2 * (size_t)n, &scratch);
+    if (rc) return rc;
+    ssq::UmiScratch sc{(ssq::u32 *)scratch, (ssq::u32 *)scratch + n};
+    const size_t smem = (size_t)ssq::kUmiSmemGroup * (8 + 8 + 4 + 4 + 1) + 16;
+    static bool configured = false;
+    if (!configured) {
+        SSQ_CUDA(cudaFuncSetAttribute(ssq::umi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = ssq::grid_for(ctx, n_groups, 2);
+    ssq::umi_cluster_kernel<<<grid, ssq::kUmiThreads, smem, ctx->stream>>>((const ssq::u64 *)words, lens, (const ssq::u64 *)counts, group_off, n_groups,
+                                                                         threshold, method, rep, n_clusters, sc);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+
+}  // extern "C"
