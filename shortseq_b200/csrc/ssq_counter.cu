@@ -1296,6 +1296,8 @@ static int prepare_regions(ssq_counter *c, int64_t n, RegionParts *rp) {
     per = (per + kLineKeys - 1) & ~(int64_t)(kLineKeys - 1);
     if (per < kLineKeys) per = kLineKeys;
     const int64_t nseg = (int64_t)kParts * slices * kParts;
+    // the count kernel addresses this buffer with 32-bit entry offsets: less slack rather than more than 2^32 entries
+    if (per * nseg >= 4000000000ll) per = (4000000000ll / nseg) & ~(int64_t)(kLineKeys - 1);
     const int64_t need = per * nseg;
     if (need > c->region_cap) {
         SSQ_CUDA(cudaStreamSynchronize(ctx->stream));
