@@ -155,6 +155,21 @@ int ssq_hamming_refset(ssq_ctx *ctx, int words_per_seq, const uint64_t *q, const
                        int64_t nq, const uint64_t *refs, const uint8_t *len_r, int32_t nr,
                        int32_t thresh, uint8_t *min_dist, uint32_t *argmin, uint32_t *n_within);
 
+/* ---- single objects (HOST pointers) -----------------------------------------
+ * The reference's per-object calls -- sq.pack(x) (short_seq.pyx:13-74), str(s) (short_seq_64.pyx:114-121,
+ * short_seq_192.pyx:114-127, short_seq_var.pyx:98-120) and a ^ b (short_seq_64.pyx:77-84 and twins) -- as
+ * batches of one ON THE DEVICE: operands travel through a page of mapped pinned memory the context owns, the call
+ * launches one small kernel on the context's stream and returns when its result has arrived (no device allocation,
+ * no copy call, no stream synchronisation).  len is 1..1024; the empty sequence never reaches the library.
+ * ssq_pack_one: words[] receives 1 (len <= 32), 3 (len <= 96) or ceil(len/32) canonical blocks, *klass the container
+ *   class; returns SSQ_ERR_BAD_BASE (and the offending position in *first_bad, may be NULL) for a base outside
+ *   {A,C,G,T} -- the reference's "Unsupported base character" -- in which case words[] must not be used.
+ * ssq_decode_one: ascii_out receives len characters.   ssq_hamming_one: both operands hold ceil(len/32) (or 1 / 3)
+ *   canonical blocks of sequences of the same length len. */
+int ssq_pack_one(ssq_ctx *ctx, const uint8_t *ascii, int32_t len, uint64_t *words, int32_t *klass, int32_t *first_bad);
+int ssq_decode_one(ssq_ctx *ctx, const uint64_t *words, int32_t len, uint8_t *ascii_out);
+int ssq_hamming_one(ssq_ctx *ctx, const uint64_t *a, const uint64_t *b, int32_t len, int32_t *dist);
+
 /* ---- dedup counting --------------------------------------------------------
  * Replaces ShortSeqCounter (counter.pyx:10-54): key = (length, words) -- the reference's
  * __eq__ (short_seq_64.pyx:41-44, short_seq_192.pyx:35-41); value = multiplicity.  The

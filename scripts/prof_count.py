@@ -19,4 +19,8 @@ for _ in range(3):
     lib.ssq_counter_clear(ctr.handle)
     _lib.check(lib.ssq_counter_pack_count(ctr.handle, ptr(b.ascii), int(b.ascii.numel()), ptr(b.offsets), n, ptr(words), ptr(lens)))
 torch.cuda.synchronize()
-print("ok", n, u, L, len(ctr))
+import ctypes as C
+d = [C.c_float(), C.c_float(), C.c_float()]
+lib.ssq_counter_last_pass_detail(ctr.handle, C.byref(d[0]), C.byref(d[1]), C.byref(d[2]))
+print("ok", n, u, L, len(ctr), "pack+scatter %.3f ms, region scatter %.3f ms, count %.3f ms" % (d[0].value, d[1].value, d[2].value),
+      os.environ.get("SSQ_LIB", ""))

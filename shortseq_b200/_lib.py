@@ -89,6 +89,9 @@ PROTOTYPES = {
     "ssq_kmers64": (_int, [_p, _int, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "ssq_normalize": (_int, [_p, _p, _i64, _p]),
     "ssq_umi_cluster": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p]),
+    "ssq_pack_one": (_int, [_p, C.c_char_p, _i32, _p, C.POINTER(_i32), C.POINTER(_i32)]),
+    "ssq_decode_one": (_int, [_p, _p, _i32, _p]),
+    "ssq_hamming_one": (_int, [_p, _p, _p, _i32, C.POINTER(_i32)]),
     "ssq_comm_unique_id": (_int, [_p]),
     "ssq_comm_init": (_int, [_p, _p, _int, _int, C.POINTER(_p)]),
     "ssq_comm_destroy": (_int, [_p]),

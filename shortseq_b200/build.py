@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libshortseq_b200.so")
-SOURCES = ["ssq_ctx.cu", "ssq_scan.cu", "ssq_pack.cu", "ssq_counter.cu", "ssq_codec.cu", "ssq_host.cu", "ssq_fastq.cu", "ssq_slice.cu", "ssq_comm.cu"]
+SOURCES = ["ssq_ctx.cu", "ssq_scan.cu", "ssq_pack.cu", "ssq_counter.cu", "ssq_codec.cu", "ssq_host.cu", "ssq_fastq.cu", "ssq_slice.cu", "ssq_comm.cu", "ssq_one.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 

@@ -1,4 +1,5 @@
 // ssq_codec.cu -- batched decode (2-bit -> ASCII), Hamming distance, synthetic reads.
+#include <stdlib.h>
 #include "ssq_internal.h"
 
 namespace ssq {
@@ -294,6 +295,117 @@ __global__ void __launch_bounds__(kThreads) decode_var_kernel(const u64 *words, 
     }
 }
 
+// ShortSeqVar decode, second version.  decode_var_kernel gives a read to a warp and a word to a lane (5 of 32 lanes
+// busy on a 150-nt read) and chains four dependent global loads per read (length -> output offset -> word offset ->
+// word).  Here a persistent CTA treats the tile's words as ONE flat list -- they are contiguous in the CSR array -- that
+// is loaded coalesced one tile ahead; thread k finds the read of word k with a 5-step search in the tile's 33 word
+// offsets (shared memory, published by warp 0 from offsets it loaded an iteration earlier) and deposits it.
+constexpr int kVar2Reads = 32;
+constexpr int kVar2Meta = 3;
+constexpr int kVar2WPT = (kVar2Reads * 32) / kThreads;      // words per thread per tile (4)
+struct DecVar2Meta {
+    int64_t t0, t1, wbase;
+    u32 orel[kVar2Reads + 1];   // first output byte of each read relative to t0 (0xFFFFFFFF: outside the tile)
+    u32 wrel[kVar2Reads + 1];   // first word of each read relative to wbase
+    u32 len[kVar2Reads];
+    int nreads, sane;
+};
+
+__global__ void __launch_bounds__(kThreads) decode_var2_kernel(const u64 *words, const int64_t *word_off,
+                                                               const uint16_t *lens, int64_t n, const int64_t *out_off,
+                                                               uint8_t *out) {
+    __shared__ u32 stream[kVarMaxChunks + 3];
+    __shared__ DecVar2Meta meta[kVar2Meta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t mis = (int64_t)((uintptr_t)out & 15);
+    const int64_t ntiles = (n + kVar2Reads - 1) / kVar2Reads;
+    const int64_t stride = gridDim.x;
+    const int mytiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + stride - 1) / stride) : 0;
+    for (int c = threadIdx.x; c < kVarMaxChunks + 3; c += kThreads) stream[c] = 0;
+
+    int64_t p_o = 0, p_w = 0, p_ol = 0, p_wl = 0;
+    u32 p_len = 0;
+    auto fetch_meta = [&](int j) {                  // warp 0: tile j's offsets into registers
+        if (j >= mytiles) return;
+        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+        const int nreads = (int)min((int64_t)kVar2Reads, n - first);
+        if (lane < nreads) { p_o = out_off[first + lane]; p_w = word_off[first + lane]; p_len = min((u32)lens[first + lane], 1024u); }
+        if (lane == 0) { p_ol = out_off[first + nreads]; p_wl = word_off[first + nreads]; }
+    };
+    auto publish = [&](int j) {                     // warp 0: registers -> shared metadata of tile j
+        if (j >= mytiles) return;
+        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+        const int nreads = (int)min((int64_t)kVar2Reads, n - first);
+        DecVar2Meta &m = meta[j % kVar2Meta];
+        const int64_t t0 = __shfl_sync(0xFFFFFFFFu, p_o, 0), wbase = __shfl_sync(0xFFFFFFFFu, p_w, 0);
+        const int64_t t1 = __shfl_sync(0xFFFFFFFFu, p_ol, 0), wend = __shfl_sync(0xFFFFFFFFu, p_wl, 0);
+        if (lane < nreads) {
+            m.orel[lane] = (p_o >= t0 && p_o + p_len <= t1) ? (u32)(p_o - t0) : 0xFFFFFFFFu;
+            m.wrel[lane] = (u32)min(max(p_w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+            m.len[lane] = p_len;
+        }
+        if (lane == 0) {
+            m.wrel[nreads] = (u32)min(max(wend - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+            m.t0 = t0; m.t1 = t1; m.wbase = wbase; m.nreads = nreads;
+            m.sane = t1 >= t0 && t1 - t0 <= (int64_t)kVar2Reads * 1024;
+        }
+    };
+    auto load_words = [&](int j, u64 (&w)[kVar2WPT]) {   // everyone: the words of tile j (its metadata is published)
+#pragma unroll
+        for (int i = 0; i < kVar2WPT; i++) w[i] = 0;
+        if (j >= mytiles) return;
+        const DecVar2Meta &m = meta[j % kVar2Meta];
+        const u32 tw = m.wrel[m.nreads];
+        const u64 *src = words + m.wbase;
+#pragma unroll
+        for (int i = 0; i < kVar2WPT; i++) {
+            const u32 k = threadIdx.x + i * kThreads;
+            if (k < tw) w[i] = src[k];
+        }
+    };
+    if (warp == 0) { fetch_meta(0); publish(0); fetch_meta(1); publish(1); fetch_meta(2); }
+    __syncthreads();
+    u64 cw[kVar2WPT];
+    load_words(0, cw);
+    for (int j = 0; j < mytiles; j++) {
+        const DecVar2Meta &m = meta[j % kVar2Meta];
+        const int64_t t0 = m.t0, t1 = m.t1;
+        const int nreads = m.nreads;
+        const bool sane = m.sane != 0;
+        const int64_t a0 = ((t0 + mis) & ~(int64_t)15) - mis;
+        if (sane) {
+            const u32 tw = m.wrel[nreads];
+#pragma unroll
+            for (int i = 0; i < kVar2WPT; i++) {
+                const u32 k = threadIdx.x + i * kThreads;
+                if (k >= tw) continue;
+                int lo_ = 0, hi_ = nreads;                    // wrel[lo_] <= k < wrel[hi_]
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (lo_ + hi_) >> 1;
+                    if (m.wrel[mid] <= k) lo_ = mid; else hi_ = mid;
+                }
+                const int jw = (int)(k - m.wrel[lo_]);
+                const int nb = 2 * (int)m.len[lo_] - 64 * jw;
+                const u32 o = m.orel[lo_];
+                if (nb > 0 && o != 0xFFFFFFFFu) {
+                    u64 w = cw[i];
+                    if (nb < 64) w &= (1ull << nb) - 1;
+                    deposit64(stream, 2 * ((int64_t)o + (t0 - a0)) + 64 * jw, w);
+                }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) { publish(j + 2); fetch_meta(j + 3); }
+        u64 nw[kVar2WPT];
+        load_words(j + 1, nw);                                 // in flight during the store phase
+        if (sane) store_tile<kThreads>(out, a0, t0, t1, stream, 3);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kVar2WPT; i++) cw[i] = nw[i];
+    }
+}
+
 // =============================================================================================
 // Hamming distance.  Replaces __xor__ (short_seq_64.pyx:77-84, short_seq_192.pyx:74-91,
 // short_seq_var.pyx:64-81).  Canonical packed words keep bits beyond 2*len zero,
@@ -534,8 +646,12 @@ int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, 
     if (n == 0) return SSQ_OK;
     SSQ_ARG(words && word_off && lens && out_offsets && ascii_out, "NULL buffer");
     DeviceGuard g(ctx->device);
-    int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, 8);
-    decode_var_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
+    static const bool v1 = getenv("SSQ_VAR_V1") != nullptr;      // development: the first version of the kernel
+    int per_sm = 8;
+    if (!v1 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_var2_kernel, kThreads, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
+    int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, per_sm);      // the second version is persistent: exactly one wave
+    if (v1) decode_var_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
+    else decode_var2_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

@@ -790,39 +790,56 @@ __global__ void __launch_bounds__(kThreads) count_parts_kernel(TableView t, Part
     block_add_new(t, my_new, s_new);
 }
 
-// ShortSeq192: the records of the level-1 partitions are inserted in partition order (table range of cap/256 slots =
-// 1/256 of the table stays in L2); block b handles the segment scatter CTA (b % num_ctas) filled for partition
-// (b / num_ctas).  A record is {w0, w1, w2, meta}, see meta192_of.
-// The last num_ctas blocks insert the scatter CTAs' overflow segments (unordered, a fraction of a percent of the reads).
+// ShortSeq192: the records of the level-1 partitions are inserted in partition order (table range of cap / kParts192
+// slots stays in L2); block b handles the segment scatter CTA (b % num_ctas) filled for partition (b / num_ctas).
+// A record is {w0, w1, w2, meta}, see meta192_of.  The last num_ctas blocks insert the scatter CTAs' overflow segments
+// (unordered, a fraction of a percent of the reads).
+// A thread takes kRecs192 records per round: the record loads are issued together, then the 32-byte loads of the home
+// slots (L2::evict_last, so that the streaming records do not push the table range out), then the compares / REDs.
+// Measured (2e8 records, 1.25e7 distinct): 1 record per thread at 8 CTAs/SM 5.65 ms, 2 at 80 registers 6.4 ms, 4 at 78
+// registers 9.9 ms -- the kernel is bound by L2 random-sector operations (one slot load + one RED per record, ~70 G/s),
+// which more independent work per thread does not raise while the lost occupancy costs.
+#ifndef SSQ_RECS192
+#define SSQ_RECS192 1
+#endif
+constexpr int kRecs192 = SSQ_RECS192;
 __global__ void __launch_bounds__(kThreads) count_parts192_kernel(TableView t, PartView pv) {
-    __shared__ u32 s_new[kThreads / 32];
     const u32 p = blockIdx.x / pv.num_ctas;
     const u32 c = blockIdx.x - p * pv.num_ctas;
-    const size_t seg = (size_t)c * kParts + p;
-    const bool overflow_seg = p >= (u32)kParts;
+    const size_t seg = (size_t)c * kParts192 + p;
+    const bool overflow_seg = p >= (u32)kParts192;
     const u32 cnt = overflow_seg ? pv.ovf_count[c] : pv.seg_count[seg];
-    const ulonglong2 *recs = reinterpret_cast<const ulonglong2 *>(overflow_seg ? pv.ovf + (size_t)c * pv.ovf_cap * 4
-                                                                               : pv.keys + seg * pv.seg_cap * 4);
-    const u64 drop = l2_policy_evict_first();
+    const u64 *recs = overflow_seg ? pv.ovf + (size_t)c * pv.ovf_cap * 4 : pv.keys + seg * pv.seg_cap * 4;
+    const u64 drop = l2_policy_evict_first(), keep = l2_policy_evict_last();
+    const int sh = 64 - t.log2_cap;
     u32 my_new = 0;
-    constexpr int kRecs = 2;     // records per thread per round
-    for (u32 i0 = 0; i0 < cnt; i0 += kThreads * kRecs) {
-        ulonglong2 a[kRecs], b[kRecs];
+    for (u32 i0 = 0; i0 < cnt; i0 += kThreads * kRecs192) {
+        u64 w0[kRecs192], w1[kRecs192], w2[kRecs192], mt[kRecs192];
 #pragma unroll
-        for (int j = 0; j < kRecs; j++) {
+        for (int j = 0; j < kRecs192; j++) {
             const u32 i = i0 + j * kThreads + threadIdx.x;
-            b[j].y = 0;
-            if (i < cnt) { a[j] = ld_hint_v2u64(recs + 2 * (size_t)i, drop); b[j] = ld_hint_v2u64(recs + 2 * (size_t)i + 1, drop); }
+            mt[j] = 0;
+            if (i < cnt) ld_stream_v4u64(recs + 4 * (size_t)i, drop, w0[j], w1[j], w2[j], mt[j]);
+        }
+        u64 sm[kRecs192], s0[kRecs192], s1[kRecs192], s2[kRecs192];
+#pragma unroll
+        for (int j = 0; j < kRecs192; j++) {
+            sm[j] = 0;
+            if (i0 + j * kThreads + threadIdx.x < cnt)
+                ld_relaxed_v4u64_hint(t.slots + 4 * ((mt[j] & ~0xFFull) >> sh), keep, sm[j], s0[j], s1[j], s2[j]);
         }
 #pragma unroll
-        for (int j = 0; j < kRecs; j++) {
+        for (int j = 0; j < kRecs192; j++) {
             if (i0 + j * kThreads + threadIdx.x >= cnt) continue;
             bool is_new = false;
-            insert192_hashed(t, b[j].y & ~0xFFull, a[j].x, a[j].y, b[j].x, (u32)(b[j].y & 0xFF) + 32, 1ull, is_new);
+            insert192_impl<true>(t, mt[j] & ~0xFFull, w0[j], w1[j], w2[j], (u32)(mt[j] & 0xFF) + 32, 1ull, is_new, sm[j], s0[j], s1[j], s2[j]);
             my_new += is_new ? 1u : 0u;
         }
     }
-    block_add_new(t, my_new, s_new);
+    // one size update per warp (a block handles ~1e4 records; no barrier at the end of a block)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
+    if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(t.size, (u64)my_new);
 }
 
 // ---- export ---------------------------------------------------------------------------------
@@ -1225,7 +1242,8 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     ssq_ctx *ctx = c->ctx;
     const int rw = c->klass == SSQ_CLASS_64 ? 1 : 4;        // 64-bit words per record
     const int line = kLineKeys / rw;                        // records per 128-byte line
-    // a CTA sees ~n/grid keys, 1/256 of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
+    const int kParts = c->klass == SSQ_CLASS_64 ? ssq::kParts : kParts192;   // level-1 partitions of this class
+    // a CTA sees ~n/grid keys, 1/kParts of them per partition: mean + 6 % + slack (overflow is handled, not fatal)
     int64_t per = n / ((int64_t)grid * kParts);
     per = per + per * env_int("SSQ_SEG_SLACK_PCT", 6, 0, 100) / 100 + env_int("SSQ_SEG_SLACK_ABS", 64, 0, 1 << 20);   // tests shrink the slack
     per = (per + line - 1) & ~(int64_t)(line - 1);
@@ -1247,7 +1265,7 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
         if (c->part_cursor) SSQ_CUDA(cudaFree(c->part_cursor));
         c->part_cursor = nullptr;
         c->part_ctas = 0;
-        SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * (size_t)grid * (kParts + 1)));
+        SSQ_CUDA(cudaMalloc(&c->part_cursor, sizeof(u32) * (size_t)grid * (ssq::kParts + 1)));
         c->part_ctas = grid;
     }
     pv->keys = c->part_keys;
@@ -1460,7 +1478,7 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
             rc = launch_count_parts(c, n, pv, c->ev[2]);
         } else {
             SSQ_CUDA(cudaEventRecord(c->ev[2], ctx->stream));
-            count_parts192_kernel<<<(kParts + 1) * pv.num_ctas, kThreads, 0, ctx->stream>>>(view_of(c), pv);
+            count_parts192_kernel<<<(kParts192 + 1) * pv.num_ctas, kThreads, 0, ctx->stream>>>(view_of(c), pv);
             SSQ_LAUNCH_CHECK();
         }
     } else {

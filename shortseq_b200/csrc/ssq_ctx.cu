@@ -114,6 +114,7 @@ int ssq_ctx_destroy(ssq_ctx *ctx) {
     cudaFree(ctx->scratch);
     cudaFree(ctx->d_report);
     cudaFreeHost(ctx->h_report);
+    if (ctx->one_host) cudaFreeHost(ctx->one_host);
     for (int i = 0; i < 2; i++) cudaStreamDestroy(ctx->copy_streams[i]);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;

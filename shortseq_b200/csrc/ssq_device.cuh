@@ -86,6 +86,14 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
 __device__ __forceinline__ void ld_relaxed_v4u64(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
     asm volatile("ld.relaxed.gpu.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
 }
+// the same with an L2 cache policy (a table range that should stay resident while a stream of records passes through)
+__device__ __forceinline__ void ld_relaxed_v4u64_hint(const u64 *p, u64 policy, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(policy) : "memory");
+}
+// 32-byte streaming load of a record that is read exactly once
+__device__ __forceinline__ void ld_stream_v4u64(const void *p, u64 policy, u64 &a, u64 &b, u64 &c, u64 &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(policy));
+}
 __device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -106,6 +114,39 @@ __device__ __forceinline__ void red_add_u32(u32 *p, u32 v) {
 }
 __device__ __forceinline__ void red_min_u64(u64 *p, u64 v) {
     asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// ---- bulk asynchronous copies (TMA, 1-D) and the mbarrier they complete on ---------------------------
+// One thread arms the barrier with the byte count and issues cp.async.bulk (SASS UBLKCP): the copy engine moves the
+// whole range global -> shared without occupying registers or issue slots; consumers wait on the barrier's phase.
+// Source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(u32 addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ---- shared memory by 32-bit shared-space address ---------------------------------------------

@@ -28,6 +28,8 @@ struct ssq_ctx {
     ssq::DevReport *d_report;     // device error record
     ssq::DevReport *h_report;     // pinned mirror
     ssq_host_staging staging;     // zero-initialised
+    void *one_host, *one_dev;     // mapped pinned page of the single-object calls (ssq_one.cu), allocated on first use
+    uint32_t one_seq;
     void *scratch;                // small device scratch (scan block totals, export cursors); grown on demand
     size_t scratch_bytes;
 };

@@ -30,9 +30,23 @@
 namespace ssq {
 
 constexpr int kPackThreads = 256;
-constexpr int kRPT = 2;                               // reads per thread per tile (fixed classes)
+constexpr int kRPT = 2;                               // reads per thread per tile (ShortSeq64)
 constexpr int kTileReads = kPackThreads * kRPT;
 constexpr int kLoadUnroll = 4;                        // 16-byte loads in flight per thread
+
+// Tile shape of pack_fixed_kernel per class.  ShortSeq64: 512 reads (<= 16 KB of ASCII = 4 prefetched 16-byte chunks per
+// thread).  ShortSeq192: 256 reads (<= 24 KB = 6 chunks per thread, all of them prefetched: with 512-read tiles more than
+// half of a tile's chunks were loaded on demand inside the encode loop, one dependent DRAM round trip after the other --
+// ncu showed the scatter-mode kernel waiting on them for 8 of every 9 issue slots at 2 CTAs per SM).
+#ifndef SSQ_LU192
+#define SSQ_LU192 6
+#endif
+template <int KLASS> struct FixedCfg {
+    static constexpr int RPT = KLASS == SSQ_CLASS_64 ? kRPT : 1;
+    static constexpr int TILE = kPackThreads * RPT;
+    static constexpr int LU = KLASS == SSQ_CLASS_64 ? kLoadUnroll : SSQ_LU192;
+    static constexpr int PARTS = KLASS == SSQ_CLASS_64 ? kParts : kParts192;
+};
 
 enum { kModePack = 0, kModeDirect = 1, kModeScatter = 2 };
 
@@ -89,10 +103,10 @@ __device__ __forceinline__ TileGeom tile_geom(const uint8_t *ascii, int64_t lo, 
 }
 
 // Issue the first kLoadUnroll rounds of 16-byte loads of an interior tile (results land in v[]).
-template <int THREADS>
-__device__ __forceinline__ void issue_tile_loads(const TileGeom &g, uint4 (&v)[kLoadUnroll]) {
+template <int THREADS, int LU = kLoadUnroll>
+__device__ __forceinline__ void issue_tile_loads(const TileGeom &g, uint4 (&v)[LU]) {
 #pragma unroll
-    for (int j = 0; j < kLoadUnroll; j++) {
+    for (int j = 0; j < LU; j++) {
         const int c = threadIdx.x + j * THREADS;
         if (c < g.nchunks) v[j] = ld_stream_v4(g.src + 16 * c);
     }
@@ -100,16 +114,16 @@ __device__ __forceinline__ void issue_tile_loads(const TileGeom &g, uint4 (&v)[k
 
 // Stage 1: codes[c] = 2-bit codes of chunk c.  `v` holds the prefetched first rounds when `prefetched`.
 // `pad` extra words after the last chunk are zeroed.  The caller must __syncthreads().
-template <int THREADS>
+template <int THREADS, int LU = kLoadUnroll>
 __device__ __forceinline__ void encode_tile(const uint8_t *ascii, int64_t lo, int64_t hi, const TileGeom &g, bool prefetched,
-                                            const uint4 (&v)[kLoadUnroll], u32 *codes, int pad, u32 &bad) {
+                                            const uint4 (&v)[LU], u32 *codes, int pad, u32 &bad) {
     if (prefetched) {
 #pragma unroll
-        for (int j = 0; j < kLoadUnroll; j++) {
+        for (int j = 0; j < LU; j++) {
             const int c = threadIdx.x + j * THREADS;
             if (c < g.nchunks) codes[c] = encode16(v[j], bad);
         }
-        for (int c = threadIdx.x + kLoadUnroll * THREADS; c < g.nchunks; c += THREADS)   // long tiles (ShortSeq192)
+        for (int c = threadIdx.x + LU * THREADS; c < g.nchunks; c += THREADS)   // tiles longer than the prefetch window
             codes[c] = encode16(ld_stream_v4(g.src + 16 * c), bad);
     } else {                                                     // first / last tile of the buffer
         for (int c = threadIdx.x; c < g.nchunks; c += THREADS) {
@@ -151,24 +165,26 @@ __device__ __noinline__ void report_len(DevReport *rep, int64_t len, u64 idx) {
 }
 
 // Offsets of one tile, held in registers so that the next tile's can be in flight during this one.
+template <int RPT>
 struct TileOffsets {
     int64_t t0, t1;
-    int64_t start[kRPT];
+    int64_t start[RPT];
     int nreads;
 };
 
-__device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets, int64_t n, int64_t tile) {
-    TileOffsets o;
-    const int64_t first = tile * kTileReads;
-    o.nreads = first < n ? (int)min((int64_t)kTileReads, n - first) : 0;
+template <int RPT>
+__device__ __forceinline__ TileOffsets<RPT> load_tile_offsets(const int64_t *offsets, int64_t n, int64_t tile) {
+    TileOffsets<RPT> o;
+    const int64_t first = tile * (kPackThreads * RPT);
+    o.nreads = first < n ? (int)min((int64_t)(kPackThreads * RPT), n - first) : 0;
     o.t0 = o.t1 = 0;
 #pragma unroll
-    for (int k = 0; k < kRPT; k++) o.start[k] = 0;
+    for (int k = 0; k < RPT; k++) o.start[k] = 0;
     if (o.nreads > 0) {
         o.t0 = offsets[first];
         o.t1 = offsets[first + o.nreads];
 #pragma unroll
-        for (int k = 0; k < kRPT; k++) {
+        for (int k = 0; k < RPT; k++) {
             const int r = threadIdx.x + k * kPackThreads;
             if (r < o.nreads) o.start[k] = offsets[first + r];
         }
@@ -178,7 +194,7 @@ __device__ __forceinline__ TileOffsets load_tile_offsets(const int64_t *offsets,
 
 // This thread's part of the test "the tile is kTileReads reads of exactly 32 bytes, the first one on a 16-byte address
 // boundary, every 16-byte chunk prefetched" (fast path of pack_fixed_kernel; all threads must agree).
-__device__ __forceinline__ bool tile_is_uniform32(const TileOffsets &o, const TileGeom &g, bool prefetched) {
+__device__ __forceinline__ bool tile_is_uniform32(const TileOffsets<kRPT> &o, const TileGeom &g, bool prefetched) {
     bool u = prefetched && o.nreads == kTileReads && g.lead == 0 && (o.t1 - o.t0) == (int64_t)kTileReads * 32;
 #pragma unroll
     for (int k = 0; k < kRPT; k++) u = u && o.start[k] == o.t0 + 32 * (int64_t)(threadIdx.x + k * kPackThreads);
@@ -193,12 +209,17 @@ __device__ __forceinline__ bool tile_is_uniform32(const TileOffsets &o, const Ti
 #ifndef SSQ_PACK_MIN_BLOCKS
 #define SSQ_PACK_MIN_BLOCKS 3
 #endif
+// ShortSeq192 with counting fused in needs ~115 registers; capped at 80 (three CTAs per SM) ptxas spills part of the
+// prefetch window, i.e. waits for the loads right where they are issued, and the kernel runs at the speed of one DRAM
+// round trip per tile (2e8 x 75 nt: 13.5 ms); uncapped at two CTAs per SM the same kernel takes 7.6 ms.
 template <int KLASS, int MODE>
-__global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+__global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE != kModePack) ? 2 : SSQ_PACK_MIN_BLOCKS) pack_fixed_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     constexpr int MAXLEN = KLASS == SSQ_CLASS_64 ? 32 : 96;
     constexpr int MINLEN = KLASS == SSQ_CLASS_64 ? 0 : 33;
     constexpr int W = KLASS == SSQ_CLASS_64 ? 1 : 3;
     constexpr int PAD = 2 * W + 1;
+    using Cfg = FixedCfg<KLASS>;
+    constexpr int kRPT = Cfg::RPT, kTileReads = Cfg::TILE, kLoadUnroll = Cfg::LU, kParts = Cfg::PARTS;   // this class's tile shape
     constexpr int MAX_CHUNKS = (kTileReads * MAXLEN + 30) / 16 + 1;
     constexpr int RW = KLASS == SSQ_CLASS_64 ? 1 : 4;     // 64-bit words per staged record (table key / {w0, w1, w2, meta})
     __shared__ u32 codes[MAX_CHUNKS + PAD];
@@ -216,7 +237,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
 
     if (MODE != kModePack && stop != nullptr && *stop != 0) return;
     if (MODE == kModeScatter) {                      // ordered by the first tile's barrier
-        stager_init(stg);
+        stager_init<kParts>(stg);
         if (threadIdx.x == 0) { s_unstaged_new = 0; s_ovf_n = 0; }
     }
 
@@ -227,14 +248,14 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     int64_t tile = blockIdx.x;
 
     // prologue: this tile's offsets and loads, the next tile's offsets
-    TileOffsets cur = load_tile_offsets(a.offsets, a.n, tile);
+    TileOffsets<kRPT> cur = load_tile_offsets<kRPT>(a.offsets, a.n, tile);
     bool cur_ok = cur.nreads > 0 && cur.t0 >= a.lo && cur.t1 >= cur.t0 && cur.t1 <= a.hi &&
                   (cur.t1 - cur.t0) <= (int64_t)kTileReads * MAXLEN;
     TileGeom geom = tile_geom(a.ascii, a.lo, a.hi, cur.t0, cur_ok ? (int)(cur.t1 - cur.t0) : 0);
     uint4 v[kLoadUnroll];
     bool prefetched = cur_ok && geom.interior;
-    if (prefetched) issue_tile_loads<kPackThreads>(geom, v);
-    TileOffsets nxt = load_tile_offsets(a.offsets, a.n, tile + stride);
+    if (prefetched) issue_tile_loads<kPackThreads, kLoadUnroll>(geom, v);
+    TileOffsets<kRPT> nxt = load_tile_offsets<kRPT>(a.offsets, a.n, tile + stride);
     // FAST PATH (ShortSeq64): a full tile of 32-nt reads whose first byte sits on a 16-byte address boundary.  Chunk c
     // of the tile is then half (c & 1) of read c >> 1, so the prefetched 16-byte chunks are encoded in registers and a
     // read's two halves meet through one shuffle between neighbouring lanes: no code stream in shared memory, no
@@ -255,10 +276,10 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
         const int tile_bytes = cur_ok ? (int)(cur.t1 - cur.t0) : 0;
         const int lead = geom.lead;
         u32 bad = 0;
-        u32 fc[kLoadUnroll];                                      // fast path: codes of this thread's four chunks
+        u32 fc[4];                                                // fast path: codes of this thread's four chunks
         if (cur_fast) {
 #pragma unroll
-            for (int j = 0; j < kLoadUnroll; j++) fc[j] = encode16(v[j], bad);
+            for (int j = 0; j < 4; j++) fc[j] = encode16(v[j], bad);
         } else if (cur_ok) {
 #pragma unroll
             for (int k = 0; k < kRPT; k++) {
@@ -267,7 +288,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                 if (r < nreads) srel[r] = (cur.start[k] >= t0 && cur.start[k] <= cur.t1) ? (u32)(cur.start[k] - t0) : 0xFFFFFFFFu;
             }
             if (threadIdx.x == 0) srel[nreads] = (u32)tile_bytes;
-            encode_tile<kPackThreads>(a.ascii, a.lo, a.hi, geom, prefetched, v, codes, PAD, bad);
+            encode_tile<kPackThreads, kLoadUnroll>(a.ascii, a.lo, a.hi, geom, prefetched, v, codes, PAD, bad);
         } else {
             // a tile whose byte range is inconsistent or larger than the staging buffer holds a read of the wrong
             // class (or offsets outside the buffer): report per read, pack nothing
@@ -288,8 +309,8 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                             (nxt.t1 - nxt.t0) <= (int64_t)kTileReads * MAXLEN;
         const TileGeom ngeom = tile_geom(a.ascii, a.lo, a.hi, nxt.t0, nxt_ok ? (int)(nxt.t1 - nxt.t0) : 0);
         const bool nprefetched = nxt_ok && ngeom.interior;
-        if (nprefetched) issue_tile_loads<kPackThreads>(ngeom, v);
-        const TileOffsets nxt2 = load_tile_offsets(a.offsets, a.n, tile + 2 * stride);
+        if (nprefetched) issue_tile_loads<kPackThreads, kLoadUnroll>(ngeom, v);
+        const TileOffsets<kRPT> nxt2 = load_tile_offsets<kRPT>(a.offsets, a.n, tile + 2 * stride);
 
         // The barrier's own vote carries "some byte was invalid"; the vote on the next tile's uniformity rides along in one
         // of three rotating shared flags: a warp that disagrees clears the flag before the barrier, thread 0 re-arms the
@@ -389,9 +410,15 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                             const u64 key = key64_of(h2, (u32)len);
                             if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
                         } else {
+#ifdef SSQ_X_NOHASH
+                            const u64 h2 = (w[0] ^ w[1] ^ w[2]) * 0x9E3779B97F4A7C15ull;
+#else
                             const u64 h2 = rotl64(hash192(w[0], w[1], w[2], (u32)len), t.rot);
+#endif
                             const u64 meta = meta192_of(h2, (u32)len);
-                            if (!stage_rec192(stg, (u32)(h2 >> 56), w[0], w[1], w[2], meta)) {
+#ifdef SSQ_X_NOSTAGE
+                            if (meta == 0x1234567ull) a.words[0] = meta;
+                            if (false && !stage_rec192(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
                                 const u32 pos = atomicAdd(&s_ovf_n, 1u);         // ring full: park the record in the overflow segment
                                 if (pos < pv.ovf_cap) {
                                     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(pv.ovf + ((size_t)blockIdx.x * pv.ovf_cap + pos) * 4);
@@ -401,6 +428,18 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                                     insert192_slow(t, h2, w[0], w[1], w[2], (u32)len, &s_unstaged_new);
                                 }
                             }
+#else
+                            if (!stage_rec192(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
+                                const u32 pos = atomicAdd(&s_ovf_n, 1u);         // ring full: park the record in the overflow segment
+                                if (pos < pv.ovf_cap) {
+                                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(pv.ovf + ((size_t)blockIdx.x * pv.ovf_cap + pos) * 4);
+                                    dst[0] = make_ulonglong2(w[0], w[1]);
+                                    dst[1] = make_ulonglong2(w[2], meta);
+                                } else {
+                                    insert192_slow(t, h2, w[0], w[1], w[2], (u32)len, &s_unstaged_new);
+                                }
+                            }
+#endif
                         }
                     }
                 }
@@ -412,7 +451,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
                 since_flush = 0;
                 flushed = true;
                 __syncthreads();
-                flush_lines<false, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                flush_lines<false, RW, kParts>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
             }
         }
         // codes[] / srel[] are rewritten by the next tile, and the rings are staged into again after a flush; a fast-path
@@ -423,7 +462,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_PACK_MIN_BLOCKS) pack_fixed_
     }
     if constexpr (MODE == kModeScatter) {
         __syncthreads();   // a fast-path tile ends without a barrier
-        flush_lines<true, RW>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+        flush_lines<true, RW, kParts>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
         __syncthreads();
         for (int p = threadIdx.x; p < kParts; p += kPackThreads)
             pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
@@ -695,9 +734,163 @@ __global__ void __launch_bounds__(kPackThreads) pack_var_kernel(PackArgs a) {
     }
 }
 
+// ---- ShortSeqVar, bulk-copy pipeline --------------------------------------------------------------
+// pack_var_kernel above gives a read to a warp and a word to a lane: a 150-nt read keeps 5 of 32 lanes busy, and every
+// tile pays three dependent global round trips (tile bounds -> bytes -> per-read offsets) with nothing in flight
+// behind them (ncu: 7 of 8 issue slots waiting on the long scoreboard, 1.8 TB/s on the 150/300/1000-nt mix).
+// Here a persistent CTA keeps kVar2Stages tiles of 32 reads in flight as 1-D bulk copies (cp.async.bulk, SASS UBLKCP):
+// one lane computes the tile's 16-byte aligned byte range from offsets it loaded one tile earlier, arms the stage's
+// mbarrier with the byte count and issues the copy -- no registers, no issue slots while the bytes travel.  Consumers
+// wait on the barrier, encode the raw bytes from shared memory into the 2-bit code stream (4:1), and then extract the
+// tile's words as ONE flat list (thread k -> word k of the tile, its read found by a 5-step search in the tile's 33
+// word offsets): every lane has work whatever the read lengths, and the word stores are fully coalesced.
+constexpr int kVar2Reads = 32;
+constexpr int kVar2Stages = 2;
+constexpr int kVar2Meta = kVar2Stages + 1;             // metadata slots: a tile's slot is rewritten only after its extraction
+constexpr int kVar2RawBytes = kVar2Reads * 1024 + 32;  // + lead (< 16) + round-up of the tail
+constexpr int kVar2MaxChunks = kVar2RawBytes / 16;
+
+struct Var2Meta {
+    int64_t t0, wbase;
+    u32 srel[kVar2Reads + 1];   // read starts relative to t0 (0xFFFFFFFF: outside the tile)
+    u32 wrel[kVar2Reads + 1];   // first word of each read relative to wbase
+    int nreads, nchunks, lead, mode;   // mode 0: inconsistent tile (skipped), 1: bytes arrive by bulk copy, 2: edge tile, guarded loads
+    int64_t a0;
+};
+
+struct Var2Smem {
+    uint8_t raw[kVar2Stages][kVar2RawBytes];
+    u32 codes[kVar2MaxChunks + 4];
+    Var2Meta meta[kVar2Meta];
+    u64 bar[kVar2Stages];
+};
+
+__global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) {
+    extern __shared__ __align__(128) uint8_t var2_dyn[];
+    Var2Smem &sm = *reinterpret_cast<Var2Smem *>(var2_dyn);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (a.n + kVar2Reads - 1) / kVar2Reads;
+    const int64_t stride = gridDim.x;
+    const int mytiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + stride - 1) / stride) : 0;
+    const u64 drop = l2_policy_evict_first();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kVar2Stages; s++) mbar_init(smem_addr(&sm.bar[s]), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer state (warp 0): the offsets of the next tile to issue, loaded one iteration ahead
+    int64_t p_off = 0, p_off_last = 0, p_woff = 0, p_woff_last = 0;
+    auto fetch_meta = [&](int j) {                  // warp 0: offsets / word offsets of this CTA's j-th tile into registers
+        if (j >= mytiles) return;
+        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+        const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
+        if (lane <= nreads) { p_off = a.offsets[first + lane]; p_woff = a.word_off[first + lane]; }
+        if (lane == 0) { p_off_last = a.offsets[first + nreads]; p_woff_last = a.word_off[first + nreads]; }
+    };
+    auto issue = [&](int j) {                       // warp 0: publish tile j's metadata, start its copy; registers hold its offsets
+        if (j >= mytiles) return;
+        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+        const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
+        Var2Meta &m = sm.meta[j % kVar2Meta];
+        const int64_t t0 = __shfl_sync(0xFFFFFFFFu, p_off, 0), wbase = __shfl_sync(0xFFFFFFFFu, p_woff, 0);
+        const int64_t t1 = __shfl_sync(0xFFFFFFFFu, p_off_last, 0), wend = __shfl_sync(0xFFFFFFFFu, p_woff_last, 0);
+        int64_t nxt = __shfl_down_sync(0xFFFFFFFFu, p_off, 1);
+        if (lane == nreads - 1) nxt = t1;
+        const bool tile_ok = t0 >= a.lo && t1 >= t0 && t1 <= a.hi && (t1 - t0) <= (int64_t)kVar2Reads * 1024 &&
+                             wend >= wbase && wend - wbase <= (int64_t)kVar2Reads * 32;
+        if (lane < nreads) {
+            const int64_t len = nxt - p_off;
+            const bool len_ok = len >= 97 && len <= 1024 && p_off >= t0 && nxt <= t1;
+            if (len < 97 || len > 1024) report_len(a.rep, len, (u64)(a.index_base + first + lane));
+            ((uint16_t *)a.lens)[first + lane] = (tile_ok && len_ok) ? (uint16_t)len : 0;
+        }
+        if (lane <= nreads) {
+            const int64_t o = lane == nreads ? t1 : p_off, w = lane == nreads ? wend : p_woff;
+            m.srel[lane] = (o >= t0 && o <= t1) ? (u32)(o - t0) : 0xFFFFFFFFu;
+            m.wrel[lane] = (u32)min(max(w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+        }
+        if (lane == 0) {
+            if (nreads == kVar2Reads) {             // entry 32 belongs to lane 0 (a warp has 32 lanes, a tile 33 boundaries)
+                m.srel[nreads] = (u32)(t1 - t0);
+                m.wrel[nreads] = (u32)min(max(wend - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+            }
+            int mode = 0;
+            TileGeom g = tile_geom(a.ascii, a.lo, a.hi, t0, tile_ok ? (int)(t1 - t0) : 0);
+            if (tile_ok) mode = g.interior ? 1 : 2;
+            else if (t0 < a.lo || t1 > a.hi || t1 < t0) atomicMin(&a.rep->first_bad_len, (u64)(a.index_base + first));
+            m.t0 = t0; m.wbase = wbase; m.nreads = nreads; m.nchunks = g.nchunks; m.lead = g.lead; m.mode = mode; m.a0 = g.a0;
+            if (mode == 1 && g.nchunks > 0) {
+                const u32 bar = smem_addr(&sm.bar[j % kVar2Stages]);
+                mbar_expect_tx(bar, 16u * (u32)g.nchunks);
+                bulk_g2s(smem_addr(sm.raw[j % kVar2Stages]), g.src, 16u * (u32)g.nchunks, bar, drop);
+            } else if (mode == 1) {
+                m.mode = 2;                         // empty byte range: nothing to copy, nothing to wait for
+            }
+        }
+    };
+    if (warp == 0) {
+        for (int j = 0; j < kVar2Stages; j++) { fetch_meta(j); issue(j); }
+        fetch_meta(kVar2Stages);
+    }
+    __syncthreads();
+
+    u32 phase = 0;                                   // bit s: parity of stage s's next completion
+    for (int j = 0; j < mytiles; j++) {
+        const int s = j % kVar2Stages;
+        const Var2Meta &m = sm.meta[j % kVar2Meta];
+        const int mode = m.mode, nchunks = m.nchunks, lead = m.lead, nreads = m.nreads;
+        const int64_t t0 = m.t0;
+        u32 bad = 0;
+        if (mode == 1) {
+            mbar_wait(smem_addr(&sm.bar[s]), (phase >> s) & 1u);
+            phase ^= 1u << s;
+            const u32 raw = smem_addr(sm.raw[s]);
+            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) sm.codes[c] = encode16(lds_v4(raw + 16 * c), bad);
+        } else if (mode == 2) {
+            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) {
+                const int64_t idx = m.a0 + 16 * (int64_t)c;
+                const uint4 x = (idx >= a.lo && idx + 16 <= a.hi) ? ld_stream_v4(a.ascii + idx) : load_chunk_guarded(a.ascii, a.lo, a.hi, idx);
+                sm.codes[c] = encode16(x, bad);
+            }
+        }
+        if (threadIdx.x < 4) sm.codes[nchunks + threadIdx.x] = 0;
+        const int tile_bad = __syncthreads_or(bad != 0);      // codes complete, raw[s] consumed
+        if (warp == 0) { issue(j + kVar2Stages); fetch_meta(j + kVar2Stages + 1); }
+        if (mode != 0) {
+            const u32 tw = m.wrel[nreads];
+            u64 *wdst = a.words + m.wbase;
+            for (u32 k = threadIdx.x; k < tw; k += kPackThreads) {
+                int lo_ = 0, hi_ = nreads;                    // wrel[lo_] <= k < wrel[hi_]
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (lo_ + hi_) >> 1;
+                    if (m.wrel[mid] <= k) lo_ = mid; else hi_ = mid;
+                }
+                const u32 r0 = m.srel[lo_], r1 = m.srel[lo_ + 1];
+                const int len = (int)(r1 - r0), jw = (int)(k - m.wrel[lo_]);
+                const bool ok = r0 != 0xFFFFFFFFu && r1 != 0xFFFFFFFFu && len >= 97 && len <= 1024;
+                wdst[k] = ok ? keep_bits(extract64(sm.codes, 2 * ((int)r0 + lead) + 64 * jw), 2 * len - 64 * jw) : 0ull;
+            }
+            if (tile_bad) {                                   // some byte near the tile is invalid: exact re-check, warp per read
+                for (int r = warp; r < nreads; r += kPackThreads / 32) {
+                    const u32 r0 = m.srel[r], r1 = m.srel[r + 1];
+                    if (r0 == 0xFFFFFFFFu || r1 == 0xFFFFFFFFu || r1 < r0 || r1 - r0 > 1024 || r1 - r0 < 97) continue;
+                    bool b = false;
+                    for (u32 q = r0 + lane; q < r1; q += 32) b |= !is_acgt(a.ascii[t0 + q]);
+                    if (__any_sync(0xFFFFFFFFu, b) && lane == 0)
+                        atomicMin(&a.rep->first_bad_base, (u64)(a.index_base + ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads + r));
+                }
+            }
+        }
+        __syncthreads();                                       // codes[] are rewritten by the next tile
+    }
+}
+
 // Persistent grid: exactly as many CTAs as are resident at once (one wave), capped by the number of tiles.
-template <int MODE>
-constexpr size_t pack_dyn_smem() { return MODE == kModeScatter ? kStagerRingBytes : 0; }
+template <int MODE, int KLASS = SSQ_CLASS_64>
+constexpr size_t pack_dyn_smem() { return MODE == kModeScatter ? (size_t)FixedCfg<KLASS>::PARTS * kRingKeys * sizeof(u64) : 0; }
 
 // The scatter mode needs 64 KB of dynamic shared memory per CTA (three CTAs per SM = most of the 227 KB).
 template <int KLASS, int MODE>
@@ -708,7 +901,7 @@ static int prepare_fixed_kernel() {
         int dev = 0;
         cudaGetDevice(&dev);
         if (!done || done_dev != dev) {
-            SSQ_CUDA(cudaFuncSetAttribute(pack_fixed_kernel<KLASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE>()));
+            SSQ_CUDA(cudaFuncSetAttribute(pack_fixed_kernel<KLASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_dyn_smem<MODE, KLASS>()));
             SSQ_CUDA(cudaFuncSetAttribute(pack_fixed_kernel<KLASS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             done = true;
             done_dev = dev;
@@ -721,9 +914,9 @@ template <int KLASS, int MODE>
 static int fixed_grid(ssq_ctx *ctx, int64_t n) {
     int per_sm = 0;
     if (prepare_fixed_kernel<KLASS, MODE>() != SSQ_OK) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_fixed_kernel<KLASS, MODE>, kPackThreads, pack_dyn_smem<MODE>()) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_fixed_kernel<KLASS, MODE>, kPackThreads, pack_dyn_smem<MODE, KLASS>()) != cudaSuccess || per_sm < 1)
         per_sm = MODE == kModeScatter ? 3 : 4;
-    return grid_for(ctx, (n + kTileReads - 1) / kTileReads, per_sm);
+    return grid_for(ctx, (n + FixedCfg<KLASS>::TILE - 1) / FixedCfg<KLASS>::TILE, per_sm);
 }
 
 // A batch of exactly 32 n bytes whose first byte is 16-byte aligned is (almost certainly) n reads of 32 nt: such
@@ -781,7 +974,7 @@ static int launch_fixed(ssq_ctx *ctx, const PackArgs &a, const TableView &t, con
     if (grid <= 0) grid = fixed_grid<KLASS, MODE>(ctx, a.n);
     int rc = prepare_fixed_kernel<KLASS, MODE>();
     if (rc) return rc;
-    pack_fixed_kernel<KLASS, MODE><<<grid, kPackThreads, pack_dyn_smem<MODE>(), ctx->stream>>>(a, t, pv, stop);
+    pack_fixed_kernel<KLASS, MODE><<<grid, kPackThreads, pack_dyn_smem<MODE, KLASS>(), ctx->stream>>>(a, t, pv, stop);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
@@ -854,9 +1047,19 @@ int ssq_packvar(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const i
     rc = scan_var_words(ctx, offsets, n, word_off);
     if (rc || n == 0) return rc;
     PackArgs a{ascii, 0, ascii_bytes, offsets, n, 0, (u64 *)words, lens, word_off, ctx->d_report};
-    int64_t ntiles = (n + kVarTileReads - 1) / kVarTileReads;
-    int grid = grid_for(ctx, ntiles, 8);
-    pack_var_kernel<<<grid, kPackThreads, 0, ctx->stream>>>(a);
+    static const bool v1 = getenv("SSQ_VAR_V1") != nullptr;      // development: the first version of the kernel
+    if (v1) {
+        int64_t ntiles = (n + kVarTileReads - 1) / kVarTileReads;
+        int grid = grid_for(ctx, ntiles, 8);
+        pack_var_kernel<<<grid, kPackThreads, 0, ctx->stream>>>(a);
+        SSQ_LAUNCH_CHECK();
+        return SSQ_OK;
+    }
+    SSQ_CUDA(cudaFuncSetAttribute(pack_var2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Var2Smem)));
+    SSQ_CUDA(cudaFuncSetAttribute(pack_var2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_var2_kernel, kPackThreads, sizeof(Var2Smem)) != cudaSuccess || per_sm < 1) per_sm = 2;
+    pack_var2_kernel<<<grid_for(ctx, (n + kVar2Reads - 1) / kVar2Reads, per_sm), kPackThreads, sizeof(Var2Smem), ctx->stream>>>(a);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

@@ -36,6 +36,10 @@ constexpr int kMinLog2Cap = 16;
 // Isolated 8-byte stores to 256 different places cost one memory transaction each (scripts/bench_scatter.cu);
 // keys are therefore staged per partition in shared memory and written as whole 128-byte lines (see Stager).
 constexpr int kParts = 256;
+#ifndef SSQ_PARTS192
+#define SSQ_PARTS192 128
+#endif
+constexpr int kParts192 = SSQ_PARTS192;    // ShortSeq192 records are 32 bytes: half the partitions keep the staging rings at 32 KB
 #ifndef SSQ_LINE_KEYS
 #define SSQ_LINE_KEYS 16
 #endif
@@ -158,20 +162,25 @@ __device__ __forceinline__ u64 slot64_h2(const TableView &t, u64 slot, u64 key, 
 // ---- ShortSeq192 -----------------------------------------------------------
 constexpr u64 kLocked = 0xFFull;
 
-// h2 = rotl(hash192(w0, w1, w2, len), rot); only its top log2(cap) bits are used
-__device__ __forceinline__ u64 insert192_hashed(const TableView &t, u64 h2, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
+// h2 = rotl(hash192(w0, w1, w2, len), rot); only its top log2(cap) bits are used.
+// PRE: (meta, a0, a1, a2) already hold a relaxed 32-byte view of the home slot (the caller issued the loads of several
+// keys' home slots together so that their latencies overlap).
+template <bool PRE>
+__device__ __forceinline__ u64 insert192_impl(const TableView &t, u64 h2, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new,
+                                              u64 meta, u64 a0, u64 a1, u64 a2) {
     const u64 mask = (1ull << t.log2_cap) - 1;
     const u64 state = (u64)(len - 32);
     u64 slot = h2 >> (64 - t.log2_cap);
     is_new = false;
     u64 probes = 0;
     const u64 limit = 1ull << t.log2_cap;
+    bool have = PRE;
     while (probes < limit) {
         u64 *p = t.slots + 4 * slot;
         // The whole slot in one 32-byte load.  A full match is conclusive (words are written once, before the state is
         // released); anything else that could be a torn view is confirmed with ordered loads below.
-        u64 meta, a0, a1, a2;
-        ld_relaxed_v4u64(p, meta, a0, a1, a2);
+        if (!have) ld_relaxed_v4u64(p, meta, a0, a1, a2);
+        have = false;
         u64 st = meta & 0xFF;
         if (st == state && a0 == w0 && a1 == w1 && a2 == w2) {
             red_add_u64(p, add << 8);
@@ -205,6 +214,10 @@ __device__ __forceinline__ u64 insert192_hashed(const TableView &t, u64 h2, u64 
     }
     atomicAdd(&t.rep->table_overflow, 1ull);
     return kNoIndex;
+}
+
+__device__ __forceinline__ u64 insert192_hashed(const TableView &t, u64 h2, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
+    return insert192_impl<false>(t, h2, w0, w1, w2, len, add, is_new, 0, 0, 0, 0);
 }
 
 __device__ __forceinline__ u64 insert192(const TableView &t, u64 w0, u64 w1, u64 w2, u32 len, u64 add, bool &is_new) {
@@ -248,8 +261,9 @@ __device__ __forceinline__ Stager make_stager(const u64 *ring, const u32 *head, 
     return Stager{smem_addr(ring), smem_addr(head), smem_addr(tail), smem_addr(list)};
 }
 
+template <int PARTS = kParts>
 __device__ __forceinline__ void stager_init(const Stager &s) {
-    for (u32 p = threadIdx.x; p < (u32)kParts; p += blockDim.x) { sts_u32(s.head + 4 * p, 0); sts_u32(s.tail + 4 * p, 0); }
+    for (u32 p = threadIdx.x; p < (u32)PARTS; p += blockDim.x) { sts_u32(s.head + 4 * p, 0); sts_u32(s.tail + 4 * p, 0); }
 }
 
 // Append one key to partition `part`.  Returns false when the ring is full (more than kRingKeys keys of one
@@ -320,7 +334,7 @@ __device__ __forceinline__ bool stage_rec192(const Stager &s, u32 part, u64 w0, 
 // 64-bit words (1: a ShortSeq64 table key, 4: a ShortSeq192 record); head / tail / seg_cap count records, a line is
 // kLineKeys / RW records; partition q's segment starts at seg0 + q * seg_cap * RW.  All threads of the CTA call this
 // between two barriers.  s_new is a shared-memory counter of keys created by the overflow path.
-template <bool FINAL, int RW = 1>
+template <bool FINAL, int RW = 1, int PARTS = kParts>
 __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_cap, const TableView &t, int fixed_top,
                                             u32 *s_new) {
     constexpr u32 kLaneGroup = kLineKeys / 2;           // lanes that copy one line (16 bytes each)
@@ -330,7 +344,7 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
     const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
     const u32 lt_mask = (1u << lane) - 1;
     const u32 list = s.list + (threadIdx.x >> 5) * 256;  // this warp's work list: ready lines as (pass << 5 | lane)
-    for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)kParts; pbase += blockDim.x) {
+    for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)PARTS; pbase += blockDim.x) {
         const u32 p = pbase + lane;
         const u32 tl = lds_u32(s.tail + 4 * p);
         const u32 hd = min(lds_u32(s.head + 4 * p), tl + kRingRecs);
@@ -347,7 +361,9 @@ __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_
             const u32 tq = lds_u32(s.tail + 4 * q) + (e >> 5) * kLineRecs;
             const u32 src = s.ring + 8 * (q * kRingKeys + (tq & (kRingRecs - 1)) * RW + 2 * sub);
             if (tq + kLineRecs <= seg_cap) {
+#ifndef SSQ_X_NOSTORE
                 *reinterpret_cast<ulonglong2 *>(seg0 + ((size_t)q * seg_cap + tq) * RW + 2 * sub) = lds_v2u64(src);
+#endif
             } else if (RW == 1) {                         // segment full
                 const u32 top = fixed_top >= 0 ? (u32)fixed_top : q;
                 const ulonglong2 v = lds_v2u64(src);

@@ -2,16 +2,22 @@
 
 Objects are immutable holders of (packed words, length) with the reference's protocol
 (reference short_seq_64.pyx:33-90, short_seq_192.pyx:27-97, short_seq_var.pyx:15-93,
-short_seq.pyx:13-238).  Packing, decoding and the Hamming operator run on the GPU through
-the batch kernels (a batch of one); equality, hashing, length and slicing are integer
-bookkeeping on the held words and stay on the host, as SURVEY section 8 row F14 assigns them.
+short_seq.pyx:13-238).  Packing, decoding and the Hamming operator run on the GPU -- as
+batches of one through the library's single-object entry points (ssq_pack_one / ssq_decode_one /
+ssq_hamming_one: one small kernel launch each, operands and results in a page of mapped pinned
+memory, no tensors); equality, hashing, length and slicing are integer bookkeeping on the held
+words and stay on the host, as SURVEY section 8 row F14 assigns them.
 """
+import ctypes as _C
+import threading as _threading
+
 import numpy as np
 import torch
 
+from . import _lib
 from . import batch as _batch
 from ._lib import CLASS_64, CLASS_192, CLASS_VAR
-from ._runtime import MSG_TOO_LONG
+from ._runtime import MSG_TOO_LONG, bad_base_message
 
 MIN_64_NT, MAX_64_NT = 0, 32
 MIN_192_NT, MAX_192_NT = 33, 96
@@ -34,6 +40,31 @@ def get_domain_var():
 
 def _nblocks(length):
     return (length + 31) // 32
+
+
+class _One:
+    """Operand buffers of the single-object calls (one set per process; the lock keeps two Python threads from
+    interleaving on them -- ctypes releases the GIL during a call)."""
+
+    def __init__(self):
+        self.ctx = _batch.context()
+        self.lib = _lib.lib()
+        self.wa = (_C.c_uint64 * 32)()
+        self.wb = (_C.c_uint64 * 32)()
+        self.klass = _C.c_int32()
+        self.bad = _C.c_int32()
+        self.text = _C.create_string_buffer(1024)
+        self.lock = _threading.Lock()
+
+
+_ONE = None
+
+
+def _one():
+    global _ONE
+    if _ONE is None:
+        _ONE = _One()
+    return _ONE
 
 
 class _ShortSeqBase:
@@ -93,13 +124,24 @@ class _ShortSeqBase:
                             f"({self._length} != {other._length})")
         if self._length == 0:
             return 0
-        d = _batch.hamming_batch(_as_array(self), _as_array(other))
-        return int(d[0])
+        o = _one()
+        with o.lock:
+            for i, w in enumerate(self._packed):
+                o.wa[i] = w
+            for i, w in enumerate(other._packed):
+                o.wb[i] = w
+            _lib.check(o.lib.ssq_hamming_one(o.ctx.handle, o.wa, o.wb, self._length, _C.byref(o.klass)))
+            return o.klass.value
 
     def __str__(self):
         if self._length == 0:
             return ""
-        return _as_array(self).decode_to_list()[0]
+        o = _one()
+        with o.lock:
+            for i, w in enumerate(self._packed):
+                o.wa[i] = w
+            _lib.check(o.lib.ssq_decode_one(o.ctx.handle, o.wa, self._length, o.text))
+            return o.text.raw[:self._length].decode("ascii")
 
     def __repr__(self):
         return f"<{type(self).__name__} ({self._length} nt): {self}>"
@@ -275,8 +317,14 @@ def _new(data: bytes):
         return empty
     if length > MAX_VAR_NT:
         raise Exception(MSG_TOO_LONG)
-    arr = _batch.pack_batch([data])
-    return arr[0]
+    o = _one()
+    with o.lock:
+        rc = o.lib.ssq_pack_one(o.ctx.handle, data, length, o.wa, _C.byref(o.klass), _C.byref(o.bad))
+        if rc == _lib.ERR_BAD_BASE:
+            raise Exception(bad_base_message(data))
+        _lib.check(rc)
+        k = o.klass.value
+        return _box(k, o.wa[:1 if k == CLASS_64 else (3 if k == CLASS_192 else _nblocks(length))], length)
 
 
 def pack(seq, /):
