@@ -744,8 +744,22 @@ __global__ void __launch_bounds__(kPackThreads) pack_var_kernel(PackArgs a) {
 // wait on the barrier, encode the raw bytes from shared memory into the 2-bit code stream (4:1), and then extract the
 // tile's words as ONE flat list (thread k -> word k of the tile, its read found by a 5-step search in the tile's 33
 // word offsets): every lane has work whatever the read lengths, and the word stores are fully coalesced.
-constexpr int kVar2Reads = 32;
-constexpr int kVar2Stages = 2;
+#ifndef SSQ_VAR2_READS
+#define SSQ_VAR2_READS 32
+#endif
+#ifndef SSQ_VAR2_STAGES
+#define SSQ_VAR2_STAGES 2
+#endif
+#ifndef SSQ_VAR2_CTAS
+#define SSQ_VAR2_CTAS 3
+#endif
+#ifndef SSQ_VAR2_CODES
+#define SSQ_VAR2_CODES 1
+#endif
+constexpr int kVar2Codes = SSQ_VAR2_CODES;             // code-stream buffers: 2 = one barrier per tile, 1 = two barriers, 8 KB less
+constexpr int kVar2Reads = SSQ_VAR2_READS;             // <= 32: lane r of warp 0 owns read r's offsets
+constexpr int kVar2Log2Reads = kVar2Reads > 16 ? 5 : (kVar2Reads > 8 ? 4 : 3);
+constexpr int kVar2Stages = SSQ_VAR2_STAGES;
 constexpr int kVar2Meta = kVar2Stages + 1;             // metadata slots: a tile's slot is rewritten only after its extraction
 constexpr int kVar2RawBytes = kVar2Reads * 1024 + 32;  // + lead (< 16) + round-up of the tail
 constexpr int kVar2MaxChunks = kVar2RawBytes / 16;
@@ -760,12 +774,12 @@ struct Var2Meta {
 
 struct Var2Smem {
     uint8_t raw[kVar2Stages][kVar2RawBytes];
-    u32 codes[kVar2MaxChunks + 4];
+    u32 codes[kVar2Codes][kVar2MaxChunks + 4];
     Var2Meta meta[kVar2Meta];
     u64 bar[kVar2Stages];
 };
 
-__global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) {
+__global__ void __launch_bounds__(kPackThreads, SSQ_VAR2_CTAS) pack_var2_kernel(PackArgs a) {
     extern __shared__ __align__(128) uint8_t var2_dyn[];
     Var2Smem &sm = *reinterpret_cast<Var2Smem *>(var2_dyn);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -780,16 +794,23 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) 
     }
     __syncthreads();
 
-    // ---- producer state (warp 0): the offsets of the next tile to issue, loaded one iteration ahead
-    int64_t p_off = 0, p_off_last = 0, p_woff = 0, p_woff_last = 0;
-    auto fetch_meta = [&](int j) {                  // warp 0: offsets / word offsets of this CTA's j-th tile into registers
+    // ---- producer state (warp 0): the offsets of the next two tiles to issue, loaded two iterations ahead (the tile
+    // loop is unrolled by two, one register set each) so that issuing a copy never waits for an offsets load.
+    // Measured on the 150/300/1000-nt mix: 32-read tiles 1.63 ms per 1e7 reads, 24-read 1.85, 16-read 2.08, 8-read 2.8 --
+    // per-tile costs (two barriers, the ragged last round of the 256-thread loops over ~730 chunks / ~365 words) favour
+    // the largest tile that still leaves three CTAs per SM; a second code buffer (one barrier per tile, two CTAs per SM)
+    // and a third stage both measured slower.
+    struct MetaRegs { int64_t p_off = 0, p_off_last = 0, p_woff = 0, p_woff_last = 0; } regs_a, regs_b;
+    auto fetch_meta = [&](int j, MetaRegs &R) {     // warp 0: offsets / word offsets of this CTA's j-th tile into registers
+        int64_t &p_off = R.p_off, &p_off_last = R.p_off_last, &p_woff = R.p_woff, &p_woff_last = R.p_woff_last;
         if (j >= mytiles) return;
         const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
         const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
         if (lane <= nreads) { p_off = a.offsets[first + lane]; p_woff = a.word_off[first + lane]; }
         if (lane == 0) { p_off_last = a.offsets[first + nreads]; p_woff_last = a.word_off[first + nreads]; }
     };
-    auto issue = [&](int j) {                       // warp 0: publish tile j's metadata, start its copy; registers hold its offsets
+    auto issue = [&](int j, const MetaRegs &R) {    // warp 0: publish tile j's metadata, start its copy; R holds its offsets
+        const int64_t p_off = R.p_off, p_off_last = R.p_off_last, p_woff = R.p_woff, p_woff_last = R.p_woff_last;
         if (j >= mytiles) return;
         const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
         const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
@@ -831,14 +852,17 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) 
         }
     };
     if (warp == 0) {
-        for (int j = 0; j < kVar2Stages; j++) { fetch_meta(j); issue(j); }
-        fetch_meta(kVar2Stages);
+        for (int j = 0; j < kVar2Stages; j++) { fetch_meta(j, regs_a); issue(j, regs_a); }
+        fetch_meta(kVar2Stages, regs_a);
+        fetch_meta(kVar2Stages + 1, regs_b);
     }
     __syncthreads();
 
     u32 phase = 0;                                   // bit s: parity of stage s's next completion
-    for (int j = 0; j < mytiles; j++) {
+    auto tile_body = [&](int j, MetaRegs &R) {      // R: offsets of tile j + kVar2Stages (refilled for tile j + kVar2Stages + 2)
+        if (j >= mytiles) return;
         const int s = j % kVar2Stages;
+        u32 *const codes = sm.codes[j % kVar2Codes];
         const Var2Meta &m = sm.meta[j % kVar2Meta];
         const int mode = m.mode, nchunks = m.nchunks, lead = m.lead, nreads = m.nreads;
         const int64_t t0 = m.t0;
@@ -847,31 +871,33 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) 
             mbar_wait(smem_addr(&sm.bar[s]), (phase >> s) & 1u);
             phase ^= 1u << s;
             const u32 raw = smem_addr(sm.raw[s]);
-            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) sm.codes[c] = encode16(lds_v4(raw + 16 * c), bad);
+            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) codes[c] = encode16(lds_v4(raw + 16 * c), bad);
         } else if (mode == 2) {
             for (int c = threadIdx.x; c < nchunks; c += kPackThreads) {
                 const int64_t idx = m.a0 + 16 * (int64_t)c;
                 const uint4 x = (idx >= a.lo && idx + 16 <= a.hi) ? ld_stream_v4(a.ascii + idx) : load_chunk_guarded(a.ascii, a.lo, a.hi, idx);
-                sm.codes[c] = encode16(x, bad);
+                codes[c] = encode16(x, bad);
             }
         }
-        if (threadIdx.x < 4) sm.codes[nchunks + threadIdx.x] = 0;
-        const int tile_bad = __syncthreads_or(bad != 0);      // codes complete, raw[s] consumed
-        if (warp == 0) { issue(j + kVar2Stages); fetch_meta(j + kVar2Stages + 1); }
+        if (threadIdx.x < 4) codes[nchunks + threadIdx.x] = 0;
+        // The only barrier of a tile: codes[j & 1] complete, raw[s] consumed.  Every thread has also finished extracting
+        // tile j - 1 (program order), so codes[(j + 1) & 1] and the metadata slot of tile j - 1 may be rewritten.
+        const int tile_bad = __syncthreads_or(bad != 0);
+        if (warp == 0) { issue(j + kVar2Stages, R); fetch_meta(j + kVar2Stages + 2, R); }
         if (mode != 0) {
             const u32 tw = m.wrel[nreads];
             u64 *wdst = a.words + m.wbase;
             for (u32 k = threadIdx.x; k < tw; k += kPackThreads) {
                 int lo_ = 0, hi_ = nreads;                    // wrel[lo_] <= k < wrel[hi_]
 #pragma unroll
-                for (int it = 0; it < 5; it++) {
+                for (int it = 0; it < kVar2Log2Reads; it++) {
                     const int mid = (lo_ + hi_) >> 1;
                     if (m.wrel[mid] <= k) lo_ = mid; else hi_ = mid;
                 }
                 const u32 r0 = m.srel[lo_], r1 = m.srel[lo_ + 1];
                 const int len = (int)(r1 - r0), jw = (int)(k - m.wrel[lo_]);
                 const bool ok = r0 != 0xFFFFFFFFu && r1 != 0xFFFFFFFFu && len >= 97 && len <= 1024;
-                wdst[k] = ok ? keep_bits(extract64(sm.codes, 2 * ((int)r0 + lead) + 64 * jw), 2 * len - 64 * jw) : 0ull;
+                wdst[k] = ok ? keep_bits(extract64(codes, 2 * ((int)r0 + lead) + 64 * jw), 2 * len - 64 * jw) : 0ull;
             }
             if (tile_bad) {                                   // some byte near the tile is invalid: exact re-check, warp per read
                 for (int r = warp; r < nreads; r += kPackThreads / 32) {
@@ -884,7 +910,11 @@ __global__ void __launch_bounds__(kPackThreads, 3) pack_var2_kernel(PackArgs a) 
                 }
             }
         }
-        __syncthreads();                                       // codes[] are rewritten by the next tile
+        if (kVar2Codes == 1) __syncthreads();          // single code buffer: the next tile's encode rewrites it
+    };
+    for (int j = 0; j < mytiles; j += 2) {
+        tile_body(j, regs_a);
+        tile_body(j + 1, regs_b);
     }
 }
 

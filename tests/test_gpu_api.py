@@ -185,3 +185,40 @@ def test_counter_shortseqvar_keys_like_the_reference(sq):
     c2 = sq.ShortSeqCounter([b"ACGT", b"GG"])
     c2._count_py_bytes_list([b"GG", b"GG", b"T"])
     assert {str(k): v for k, v in c2.items()} == {"ACGT": 1, "GG": 3, "T": 1}
+
+
+def test_single_object_entry_points_vs_oracle(sq, oracle):
+    """ssq_pack_one / ssq_decode_one / ssq_hamming_one through the C ABI (ctypes): every length 1..1024 (step 7, plus the
+    class boundaries) against the oracle's pack_one, decode round trip, Hamming against a mutated copy, bad bases."""
+    import ctypes as C
+    from shortseq_b200 import _lib
+    from shortseq_b200._runtime import context
+    lib, ctx = _lib.lib(), context()
+    rng = random.Random(11)
+    wa, wb = (C.c_uint64 * 32)(), (C.c_uint64 * 32)()
+    klass, bad, dist = C.c_int32(), C.c_int32(), C.c_int32()
+    text = C.create_string_buffer(1024)
+    for n in sorted(set(list(range(1, 1025, 7)) + [31, 32, 33, 95, 96, 97, 1023, 1024])):
+        s = rand_seq(rng, n).encode()
+        assert lib.ssq_pack_one(ctx.handle, s, n, wa, C.byref(klass), C.byref(bad)) == 0
+        oklass, ow = oracle.pack_one(s)
+        nw = 1 if n <= 32 else (3 if n <= 96 else (n + 31) // 32)
+        assert klass.value == oklass and bad.value == -1
+        assert [int(x) for x in wa[:nw]] == [int(x) for x in ow[:nw]], n
+        assert lib.ssq_decode_one(ctx.handle, wa, n, text) == 0 and text.raw[:n] == s
+        # mutate k positions: distance k
+        k = rng.randint(0, min(n, 9))
+        t = bytearray(s)
+        for p in rng.sample(range(n), k):
+            t[p] = ord({"A": "C", "C": "G", "G": "T", "T": "A"}[chr(t[p])])
+        assert lib.ssq_pack_one(ctx.handle, bytes(t), n, wb, C.byref(klass), None) == 0
+        assert lib.ssq_hamming_one(ctx.handle, wa, wb, n, C.byref(dist)) == 0 and dist.value == k
+    for n, pos in ((5, 0), (32, 31), (75, 40), (300, 299)):
+        t = bytearray(rand_seq(rng, n).encode())
+        t[pos] = ord("N")
+        assert lib.ssq_pack_one(ctx.handle, bytes(t), n, wa, C.byref(klass), C.byref(bad)) == _lib.ERR_BAD_BASE
+        assert bad.value == pos
+        with pytest.raises(Exception, match="Unsupported base character"):
+            sq.pack(bytes(t))
+    assert lib.ssq_pack_one(ctx.handle, b"A", 0, wa, C.byref(klass), None) == _lib.ERR_ARG
+    assert lib.ssq_pack_one(ctx.handle, b"A" * 1025, 1025, wa, C.byref(klass), None) == _lib.ERR_ARG
