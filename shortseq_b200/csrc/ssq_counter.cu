@@ -1277,8 +1277,8 @@ static int prepare_parts(ssq_counter *c, int64_t n, int grid, PartView *pv) {
     pv->ovf_cap = (u32)ovf_cap;
     // a tile brings 512 keys = 2 per partition on average and a ring holds 32: flushing every 4th tile keeps ring
     // overflow (handled, but slow) below one key in a thousand tiles
-    // (ShortSeq192 rings hold 8 records: flush after every tile)
-    pv->flush_every = c->klass == SSQ_CLASS_64 ? (u32)env_int("SSQ_FLUSH_EVERY", 4, 1, 8) : 1u;
+    // (ShortSeq192: a 256-read tile brings 2 records per partition and a ring holds 16: flush every second tile)
+    pv->flush_every = c->klass == SSQ_CLASS_64 ? (u32)env_int("SSQ_FLUSH_EVERY", 4, 1, 8) : (u32)env_int("SSQ_FLUSH_EVERY192", kRingKeys192 >= 64 ? 2 : 1, 1, 8);
     return SSQ_OK;
 }
 

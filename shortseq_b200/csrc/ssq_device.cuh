@@ -40,11 +40,11 @@ __host__ __device__ __forceinline__ u64 unmix64(u64 x) {
 __host__ __device__ __forceinline__ u64 rotl64(u64 x, int r) { return r ? (x << r) | (x >> (64 - r)) : x; }
 __host__ __device__ __forceinline__ u64 rotr64(u64 x, int r) { return r ? (x >> r) | (x << (64 - r)) : x; }
 
-// Slot hash of a 3-word key (ShortSeq192).  Not a bijection; the key is stored verbatim.
+// Slot hash of a 3-word key (ShortSeq192).  Not a bijection; the key is stored verbatim.  The three words are folded
+// with odd rotations (a 2-bit code never lines up with itself) and one multiply before a single splitmix round: the
+// first version ran three rounds (six 64-bit multiplies) and was 12 % of the fused pack+scatter kernel's instructions.
 __host__ __device__ __forceinline__ u64 hash192(u64 w0, u64 w1, u64 w2, u32 len) {
-    u64 h = mix64(w2 ^ ((u64)len * 0x9E3779B97F4A7C15ull));
-    h = mix64(h ^ w1);
-    return mix64(h ^ w0);
+    return mix64(w0 ^ rotl64(w1, 21) ^ (rotl64(w2, 43) * 0x9E3779B97F4A7C15ull) ^ ((u64)len << 56));
 }
 
 // ---- memory intrinsics ---------------------------------------------------------

@@ -46,6 +46,7 @@ template <int KLASS> struct FixedCfg {
     static constexpr int TILE = kPackThreads * RPT;
     static constexpr int LU = KLASS == SSQ_CLASS_64 ? kLoadUnroll : SSQ_LU192;
     static constexpr int PARTS = KLASS == SSQ_CLASS_64 ? kParts : kParts192;
+    static constexpr int RING = KLASS == SSQ_CLASS_64 ? kRingKeys : kRingKeys192;   // staging ring per partition, in 64-bit words
 };
 
 enum { kModePack = 0, kModeDirect = 1, kModeScatter = 2 };
@@ -229,7 +230,8 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
-    __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 64 : 1];
+    constexpr int kRing = Cfg::RING;
+    __shared__ u32 s_list[MODE == kModeScatter ? (kPackThreads / 32) * 32 * (kRing / kLineKeys) : 1];
     __shared__ u32 s_unstaged_new, s_ovf_n;
     __shared__ u32 s_uni[3];                            // fast-path votes, see the tile loop
     const Stager stg = make_stager(dyn_ring, s_head, s_tail, s_list);
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
                             const u64 meta = meta192_of(h2, (u32)len);
 #ifdef SSQ_X_NOSTAGE
                             if (meta == 0x1234567ull) a.words[0] = meta;
-                            if (false && !stage_rec192(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
+                            if (false && !stage_rec192<kRing>(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
                                 const u32 pos = atomicAdd(&s_ovf_n, 1u);         // ring full: park the record in the overflow segment
                                 if (pos < pv.ovf_cap) {
                                     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(pv.ovf + ((size_t)blockIdx.x * pv.ovf_cap + pos) * 4);
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
                                 }
                             }
 #else
-                            if (!stage_rec192(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
+                            if (!stage_rec192<kRing>(stg, (u32)(h2 >> (kParts192 == 128 ? 57 : 56)), w[0], w[1], w[2], meta)) {
                                 const u32 pos = atomicAdd(&s_ovf_n, 1u);         // ring full: park the record in the overflow segment
                                 if (pos < pv.ovf_cap) {
                                     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(pv.ovf + ((size_t)blockIdx.x * pv.ovf_cap + pos) * 4);
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
                 since_flush = 0;
                 flushed = true;
                 __syncthreads();
-                flush_lines<false, RW, kParts>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+                flush_lines<false, RW, kParts, kRing>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
             }
         }
         // codes[] / srel[] are rewritten by the next tile, and the rings are staged into again after a flush; a fast-path
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
     }
     if constexpr (MODE == kModeScatter) {
         __syncthreads();   // a fast-path tile ends without a barrier
-        flush_lines<true, RW, kParts>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
+        flush_lines<true, RW, kParts, kRing>(stg, seg0, pv.seg_cap, t, -1, &s_unstaged_new);
         __syncthreads();
         for (int p = threadIdx.x; p < kParts; p += kPackThreads)
             pv.seg_count[(size_t)blockIdx.x * kParts + p] = stager_seg_count(stg, p, pv.seg_cap);
@@ -920,7 +922,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_VAR2_CTAS) pack_var2_kernel(
 
 // Persistent grid: exactly as many CTAs as are resident at once (one wave), capped by the number of tiles.
 template <int MODE, int KLASS = SSQ_CLASS_64>
-constexpr size_t pack_dyn_smem() { return MODE == kModeScatter ? (size_t)FixedCfg<KLASS>::PARTS * kRingKeys * sizeof(u64) : 0; }
+constexpr size_t pack_dyn_smem() { return MODE == kModeScatter ? (size_t)FixedCfg<KLASS>::PARTS * FixedCfg<KLASS>::RING * sizeof(u64) : 0; }
 
 // The scatter mode needs 64 KB of dynamic shared memory per CTA (three CTAs per SM = most of the 227 KB).
 template <int KLASS, int MODE>

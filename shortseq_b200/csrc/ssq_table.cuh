@@ -45,6 +45,10 @@ constexpr int kParts192 = SSQ_PARTS192;    // ShortSeq192 records are 32 bytes: 
 #endif
 constexpr int kLineKeys = SSQ_LINE_KEYS;   // keys per flushed line (16 keys = 128 bytes)
 constexpr int kRingKeys = 2 * kLineKeys;   // staging ring per partition per CTA
+#ifndef SSQ_RING192
+#define SSQ_RING192 64
+#endif
+constexpr int kRingKeys192 = SSQ_RING192;  // ShortSeq192: ring of kRingKeys192 / 4 records (16 records = 4 lines) per partition
 constexpr size_t kStagerRingBytes = (size_t)kParts * kRingKeys * sizeof(u64);   // 64 KB of dynamic shared memory
 struct PartView {
     u64 *keys;          // [num_ctas][kParts][seg_cap] table keys (key64_of) awaiting insertion
@@ -254,7 +258,7 @@ struct Stager {      // 32-bit shared-space addresses (see smem_addr)
     u32 ring;      // u64 [kParts][kRingKeys]
     u32 head;      // u32 [kParts]
     u32 tail;      // u32 [kParts]
-    u32 list;      // u32 [warps][64] scratch of flush_lines
+    u32 list;      // u32 [warps][32 * lines per ring] scratch of flush_lines
 };
 
 __device__ __forceinline__ Stager make_stager(const u64 *ring, const u32 *head, const u32 *tail, const u32 *list) {
@@ -319,12 +323,13 @@ static __device__ __noinline__ void insert64_slow(const TableView &t, u64 h2, u6
     if (is_new) atomicAdd(my_new, 1u);
 }
 
-// Append one ShortSeq192 record to partition `part` (ring of kRingKeys / 4 records).
+// Append one ShortSeq192 record to partition `part` (ring of RING / 4 records).
+template <int RING = kRingKeys192>
 __device__ __forceinline__ bool stage_rec192(const Stager &s, u32 part, u64 w0, u64 w1, u64 w2, u64 meta) {
-    constexpr u32 kRingRecs = kRingKeys / 4;
+    constexpr u32 kRingRecs = RING / 4;
     const u32 pos = atoms_add_u32(s.head + 4 * part, 1u);
     if (pos - lds_u32(s.tail + 4 * part) >= kRingRecs) return false;
-    const u32 a = s.ring + 8 * (part * kRingKeys + (pos & (kRingRecs - 1)) * 4);
+    const u32 a = s.ring + 8 * (part * RING + (pos & (kRingRecs - 1)) * 4);
     asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(a), "l"(w0), "l"(w1) : "memory");
     asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(a + 16), "l"(w2), "l"(meta) : "memory");
     return true;
@@ -334,26 +339,31 @@ __device__ __forceinline__ bool stage_rec192(const Stager &s, u32 part, u64 w0, 
 // 64-bit words (1: a ShortSeq64 table key, 4: a ShortSeq192 record); head / tail / seg_cap count records, a line is
 // kLineKeys / RW records; partition q's segment starts at seg0 + q * seg_cap * RW.  All threads of the CTA call this
 // between two barriers.  s_new is a shared-memory counter of keys created by the overflow path.
-template <bool FINAL, int RW = 1, int PARTS = kParts>
+template <bool FINAL, int RW = 1, int PARTS = kParts, int RING = kRingKeys>
 __device__ __forceinline__ void flush_lines(const Stager &s, u64 *seg0, u32 seg_cap, const TableView &t, int fixed_top,
                                             u32 *s_new) {
     constexpr u32 kLaneGroup = kLineKeys / 2;           // lanes that copy one line (16 bytes each)
     constexpr u32 kGroups = 32 / kLaneGroup;            // lines per warp-wide store
-    constexpr u32 kRingRecs = kRingKeys / RW, kLineRecs = kLineKeys / RW;
+    constexpr u32 kRingRecs = RING / RW, kLineRecs = kLineKeys / RW;
+    constexpr u32 kRingKeys = RING;                     // this instantiation's ring size shadows the default
     const u32 lane = threadIdx.x & 31;
     const u32 g = lane / kLaneGroup, sub = lane % kLaneGroup;
     const u32 lt_mask = (1u << lane) - 1;
-    const u32 list = s.list + (threadIdx.x >> 5) * 256;  // this warp's work list: ready lines as (pass << 5 | lane)
+    constexpr u32 kMaxLines = RING / kLineKeys;         // complete lines a ring can hold (2; 4 for ShortSeq192)
+    const u32 list = s.list + (threadIdx.x >> 5) * (32 * kMaxLines * 4);  // this warp's work list: ready lines as (line << 5 | lane)
     for (u32 pbase = (threadIdx.x >> 5) * 32; pbase < (u32)PARTS; pbase += blockDim.x) {
         const u32 p = pbase + lane;
         const u32 tl = lds_u32(s.tail + 4 * p);
         const u32 hd = min(lds_u32(s.head + 4 * p), tl + kRingRecs);
         const u32 avail = hd - tl;
-        const u32 nl = avail / kLineRecs;               // 0, 1 or 2 complete lines
-        const u32 m1 = __ballot_sync(0xFFFFFFFFu, nl > 0), m2 = __ballot_sync(0xFFFFFFFFu, nl > 1);
-        const u32 n1 = __popc(m1), nready = n1 + __popc(m2);
-        if (nl > 0) sts_u32(list + 4 * __popc(m1 & lt_mask), lane);
-        if (nl > 1) sts_u32(list + 4 * (n1 + __popc(m2 & lt_mask)), 32u | lane);
+        const u32 nl = avail / kLineRecs;               // 0 .. kMaxLines complete lines
+        u32 nready = 0;
+#pragma unroll
+        for (u32 l = 0; l < kMaxLines; l++) {
+            const u32 m = __ballot_sync(0xFFFFFFFFu, nl > l);
+            if (nl > l) sts_u32(list + 4 * (nready + __popc(m & lt_mask)), (l << 5) | lane);
+            nready += __popc(m);
+        }
         __syncwarp();
         for (u32 it = g; it < nready; it += kGroups) {   // group g copies the lines it, it + kGroups, ...
             const u32 e = lds_u32(list + 4 * it);

@@ -1,8 +1,8 @@
 """Host-side (numpy) statement of the counter's key hash: which hash partition / rank owns a key.
 
 The device tables mix their own slot hash (the reference's dict hash, word0, is never
-observable): splitmix64 of the packed word for ShortSeq64 keys, a three-round mix of the
-words and the length for ShortSeq192 keys (csrc/ssq_device.cuh).  The owner of a key in a
+observable): splitmix64 of the packed word for ShortSeq64 keys, a rotate-fold of the three
+words and the length followed by one splitmix64 round for ShortSeq192 keys (csrc/ssq_device.cuh).  The owner of a key in a
 P-way multi-GPU merge is the top log2(P) bits of that hash.  This module only computes
 partition ids for bookkeeping and tests; it counts nothing.
 """
@@ -29,10 +29,11 @@ def key_hash(words, lens, klass):
     words = np.asarray(words, dtype=np.uint64)
     if klass == 0:
         return mix64(words)
+    def rotl(x, r):
+        return (x << np.uint64(r)) | (x >> np.uint64(64 - r))
     with np.errstate(over="ignore"):
-        h = mix64(words[:, 2] ^ (np.asarray(lens, dtype=np.uint64) * _GOLD))
-    h = mix64(h ^ words[:, 1])
-    return mix64(h ^ words[:, 0])
+        return mix64(words[:, 0] ^ rotl(words[:, 1], 21) ^ (rotl(words[:, 2], 43) * _GOLD)
+                     ^ (np.asarray(lens, dtype=np.uint64) << np.uint64(56)))
 
 
 def owner_rank(words, lens, klass, world):
