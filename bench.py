@@ -482,12 +482,15 @@ def cfg_c3(sq, args, peak, world, rank, state):
     if world > 1:
         owner = sq.DeviceCounter(sq.CLASS_192, expected_unique=int(1.1 * u / world) + 1024, hash_rot=world.bit_length() - 1)
 
+    xms = []
+
     def step():
         pt.step()
         if world > 1:
             pt._lib.check(pt.lib.ssq_counter_clear(owner.handle))
             if state["comm"] is not None:
                 state["comm"].merge(pt.counter, owner)        # ShortSeq192: grouped ncclSend / ncclRecv inside the library
+                xms.append((state["comm"].exchange_ms, state["comm"].merge_ms))
             else:
                 merge_alltoall(pt.counter, owner=owner)
             return len(owner)
@@ -525,6 +528,9 @@ def cfg_c3(sq, args, peak, world, rank, state):
            "pass_ms_rank0": round(pass_ms, 3), "kernel_ms": {"pack+scatter": round(ph[0], 3), "count": round(ph[1] + ph[2], 3)},
            "pass_frac": round(pt.pass_bytes(local_unique) / (pass_ms * 1e-3) / 1e9 / peak, 4),
            "scaling": "strong", "status": rep.code, "parity_check": pc}
+    if xms:
+        res["exchange_ms"] = round(statistics.mean(x[0] for x in xms[-K:]), 3)
+        res["merge_ms"] = round(statistics.mean(x[1] for x in xms[-K:]), 3)
     del pt, owner
     free_gpu()
     return res

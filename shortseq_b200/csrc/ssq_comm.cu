@@ -31,6 +31,8 @@ namespace ssq {
 int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *block_counts,
                                const int64_t *block_regions, int n_blocks, const int64_t *region_bases, int64_t rb_stride,
                                const u64 *flags, u64 epoch);
+int counter_export_count_pass(ssq_counter *c, int n_parts, int64_t *part_counts);
+int counter_export_scatter_to(ssq_counter *c, int n_parts, u64 *const *dst_words, uint8_t *const *dst_lens, u64 *const *dst_counts);
 
 struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId;
@@ -306,12 +308,18 @@ int ssq_counter_merge_alltoall(ssq_comm *cm, ssq_counter *local, ssq_counter *ow
     ssq_counter_regions(local, &local_regions);
     const bool region_export = local->klass == SSQ_CLASS_64 && local_regions >= P;
     bool peer = cm->peer_ok && region_export;
+    // ShortSeq192 tables have no regions: two passes over the table (count, then scatter), but the scatter pass stores
+    // straight into the owners' buffers too -- same arrival flags, weighted insert on the owner
+    const bool peer2 = cm->peer_ok && !region_export;
     int rc;
 
     // ---- 1. sizes ---------------------------------------------------------------------------------------------
     int64_t n_local = 0;
     if (region_export) {
         rc = ssq_counter_export_counts(local, P, cm->d_mine);                 // from the region occupancy, no table pass
+        if (rc) return rc;
+    } else if (peer2) {
+        rc = counter_export_count_pass(local, P, cm->d_mine);
         if (rc) return rc;
     } else {
         rc = ssq_counter_size(local, &n_local);                                // staged path: the export counts while it groups
@@ -350,6 +358,28 @@ int ssq_counter_merge_alltoall(ssq_comm *cm, ssq_counter *local, ssq_counter *ow
     cm->epoch++;
     SSQ_CUDA(cudaEventRecord(cm->ev[0], st));
 
+    if (!peer && peer2 && cm->peer_ok) {
+        // ---- ShortSeq192 over peer memory: scatter pass of the export = exchange, flags, weighted insert on the owner ----
+        const int64_t rb_stride = cm->rb_cap + 1;
+        for (int d = 0; d < P; d++) {
+            cm->h_table[0 * P + d] = (int64_t)((uint64_t *)cm->peer[kBufWords][d] + before_me[d] * W);
+            cm->h_table[1 * P + d] = (int64_t)((uint8_t *)cm->peer[kBufLens][d] + before_me[d]);
+            cm->h_table[2 * P + d] = (int64_t)((uint64_t *)cm->peer[kBufCounts][d] + before_me[d]);
+            cm->h_table[4 * P + d] = (int64_t)cm->peer[kBufFlags][d];
+        }
+        SSQ_CUDA(cudaMemcpyAsync(cm->d_table, cm->h_table, 8 * 5 * (size_t)P, cudaMemcpyHostToDevice, st));
+        rc = counter_export_scatter_to(local, P, (u64 *const *)(cm->d_table), (uint8_t *const *)(cm->d_table + P), (u64 *const *)(cm->d_table + 2 * P));
+        if (rc) return rc;
+        signal_kernel<<<1, 32, 0, st>>>((u64 *const *)(cm->d_table + 4 * P), P, me, cm->epoch);
+        SSQ_LAUNCH_CHECK();
+        SSQ_CUDA(cudaEventRecord(cm->ev[1], st));
+        for (int s = 0; s < P; s++) block_regions[s] = 0;     // no region grid: counter_merge_regions_impl takes its plain path
+        rc = counter_merge_regions_impl(owner, (const u64 *)cm->mine[kBufWords], (const uint8_t *)cm->mine[kBufLens],
+                                        (const u64 *)cm->mine[kBufCounts], block_counts, block_regions, P,
+                                        (const int64_t *)cm->mine[kBufBases], rb_stride, (const u64 *)cm->mine[kBufFlags], cm->epoch);
+        if (rc) return rc;
+    } else
+
     if (peer) {
         // ---- 2. export = exchange: peer stores, then the arrival flags -------------------------------------------
         const int64_t rb_stride = cm->rb_cap + 1;
@@ -377,7 +407,7 @@ int ssq_counter_merge_alltoall(ssq_comm *cm, ssq_counter *local, ssq_counter *ow
         if (rc) return rc;
     } else {
         // ---- staged path: all-to-all-v of the grouped export with grouped ncclSend / ncclRecv --------------------
-        if (region_export) {            // the sizes came from the region occupancy: export now
+        if (region_export || peer2) {   // the sizes came from the region occupancy / the count pass: export now
             rc = ssq_counter_size(local, &n_local);
             if (rc) return rc;
             rc = ensure_stage(cm, n_local, W);

@@ -909,10 +909,46 @@ __global__ void export_bases_kernel(const u64 *part_counts, u64 *cursors, int np
     for (int p = 0; p < nparts; p++) { cursors[p] = run; run += part_counts[p]; }
 }
 
+// Coalesced copy of n 64-bit words / bytes from shared memory to global memory (possibly another GPU's): the bulk leaves as
+// aligned 16-byte stores by consecutive threads -- fine-grained 8-byte stores cost one NVLink packet each.
+__device__ __forceinline__ void copy_out_u64(u64 *dst, const u64 *sm, u32 n) {
+    const u32 head = (((uintptr_t)dst & 15) != 0 && n > 0) ? 1u : 0u;
+    if (head && threadIdx.x == 0) dst[0] = sm[0];
+    const u32 pairs = (n - head) / 2;
+    for (u32 i = threadIdx.x; i < pairs; i += blockDim.x)
+        *reinterpret_cast<ulonglong2 *>(dst + head + 2 * i) = make_ulonglong2(sm[head + 2 * i], sm[head + 2 * i + 1]);
+    if (((n - head) & 1) && threadIdx.x == 32) dst[n - 1] = sm[n - 1];
+}
+__device__ __forceinline__ void copy_out_u8(uint8_t *dst, const uint8_t *sm, u32 n) {
+    const u32 head = min(n, (u32)((16 - ((uintptr_t)dst & 15)) & 15));
+    if (threadIdx.x < head) dst[threadIdx.x] = sm[threadIdx.x];
+    const u32 vecs = (n - head) / 16;
+    for (u32 i = threadIdx.x; i < vecs; i += blockDim.x) {
+        const uint8_t *p = sm + head + 16 * i;
+        u32 w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = (u32)p[4 * k] | ((u32)p[4 * k + 1] << 8) | ((u32)p[4 * k + 2] << 16) | ((u32)p[4 * k + 3] << 24);
+        *reinterpret_cast<uint4 *>(dst + head + 16 * i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    const u32 done = head + 16 * vecs;
+    if (threadIdx.x < n - done) dst[done + threadIdx.x] = sm[done + threadIdx.x];
+}
+
+// pw / pl / pc (all or none): per-partition destination arrays -- partition p's tuples go to pw[p] / pl[p] / pc[p], which
+// may be another GPU's memory (the ShortSeq192 send side of ssq_counter_merge_alltoall); the cursors then start at 0.
 template <int KLASS>
 __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, int log2_parts,
                                                                   u64 *cursors, u64 *words, uint8_t *lens, u64 *counts,
-                                                                  int64_t *first_idx) {
+                                                                  int64_t *first_idx, u64 *const *pw = nullptr,
+                                                                  uint8_t *const *pl = nullptr, u64 *const *pc = nullptr) {
+    // dynamic shared memory (optional): staging of a one-partition tile's tuples in output order -- words | counts | lens
+    extern __shared__ __align__(16) u64 dyn_stage[];
+    constexpr int kTileSlots = kThreads * kExportItems;
+    constexpr int EW = KLASS == SSQ_CLASS_64 ? 1 : 3;
+    const bool staged_out = first_idx == nullptr && pw != nullptr;       // the launch provided the staging space
+    u64 *const st_words = dyn_stage, *const st_counts = dyn_stage + (size_t)EW * kTileSlots;
+    uint8_t *const st_lens = reinterpret_cast<uint8_t *>(dyn_stage + (size_t)(EW + 1) * kTileSlots);
+    __shared__ u32 s_total;
     __shared__ u32 cnt[kMaxParts];
     __shared__ u64 base[kMaxParts];
     __shared__ u32 s_part[2];
@@ -955,7 +991,7 @@ __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, i
             __syncthreads();
             u32 before = 0, total = 0;
             for (int w = 0; w < kThreads / 32; w++) { if (w < (int)warp) before += s_warp[w]; total += s_warp[w]; }
-            if (threadIdx.x == 0) base[0] = total ? atomicAdd(&cursors[s_part[0]], (u64)total) : 0;
+            if (threadIdx.x == 0) { base[0] = total ? atomicAdd(&cursors[s_part[0]], (u64)total) : 0; s_total = total; }
             __syncthreads();
             u32 run = before + incl - n_used;
 #pragma unroll
@@ -970,14 +1006,39 @@ __global__ void __launch_bounds__(kThreads) export_scatter_kernel(TableView t, i
                 base[p] = cnt[p] ? atomicAdd(&cursors[p], (u64)cnt[p]) : 0;   // cursors start at the partition bases
             __syncthreads();
         }
+        const u32 tile_part = one_part ? s_part[0] : 0u;     // the partition every entry of a one-partition tile belongs to
+        if (staged_out && one_part) {
+            // the tile's tuples are one contiguous output range: order them in shared memory, copy out coalesced
+#pragma unroll
+            for (int k = 0; k < kExportItems; k++) {
+                if (!r[k].used) continue;
+                const u32 o = rank[k];
+                if constexpr (KLASS == SSQ_CLASS_64) st_words[o] = r[k].w0;
+                else { st_words[3 * o] = r[k].w0; st_words[3 * o + 1] = r[k].w1; st_words[3 * o + 2] = r[k].w2; }
+                st_counts[o] = r[k].count;
+                st_lens[o] = (uint8_t)r[k].len;
+            }
+            __syncthreads();
+            const u32 total = s_total;
+            if (total) {
+                const u64 b0 = base[0];
+                copy_out_u64(pw[tile_part] + (size_t)EW * b0, st_words, EW * total);
+                copy_out_u64(pc[tile_part] + b0, st_counts, total);
+                copy_out_u8(pl[tile_part] + b0, st_lens, total);
+            }
+            __syncthreads();
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < kExportItems; k++) {
             if (!r[k].used) continue;
             u64 o = base[r[k].part] + rank[k];
-            if constexpr (KLASS == SSQ_CLASS_64) words[o] = r[k].w0;
-            else { words[3 * o] = r[k].w0; words[3 * o + 1] = r[k].w1; words[3 * o + 2] = r[k].w2; }
-            lens[o] = (uint8_t)r[k].len;
-            counts[o] = r[k].count;
+            u64 *wd = words; uint8_t *ld = lens; u64 *cd = counts;
+            if (pw != nullptr) { const u32 dp = one_part ? tile_part : r[k].part; wd = pw[dp]; ld = pl[dp]; cd = pc[dp]; }
+            if constexpr (KLASS == SSQ_CLASS_64) wd[o] = r[k].w0;
+            else { wd[3 * o] = r[k].w0; wd[3 * o + 1] = r[k].w1; wd[3 * o + 2] = r[k].w2; }
+            ld[o] = (uint8_t)r[k].len;
+            cd[o] = r[k].count;
             if (first_idx) first_idx[o] = (int64_t)r[k].first;
         }
         __syncthreads();
@@ -1806,6 +1867,53 @@ int ssq_counter_export(ssq_counter *c, int n_parts, uint64_t *words, uint8_t *le
     if (e != cudaSuccess) return cuda_fail(e, "export kernels", __FILE__, __LINE__);
     return SSQ_OK;
 }
+
+}  // extern "C"
+
+namespace ssq {
+// Two-pass export of a table without regions (ShortSeq192), split for the multi-GPU exchange (ssq_comm.cu):
+// counter_export_count_pass fills part_counts[n_parts] (pass 1 over the table); counter_export_scatter_to then stores
+// partition p's tuples at dst_*[p] (pass 2), which may be peer memory.  Nothing may change the table in between.
+int counter_export_count_pass(ssq_counter *c, int n_parts, int64_t *part_counts) {
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    ssq_ctx *ctx = c->ctx;
+    const int64_t cap = (int64_t)1 << c->log2_cap;
+    SSQ_CUDA(cudaMemsetAsync(part_counts, 0, n_parts * sizeof(u64), ctx->stream));
+    const int grid = grid_for(ctx, cap / kThreads, 8);
+    if (c->klass == SSQ_CLASS_64) export_count_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), log2_parts, (u64 *)part_counts);
+    else export_count_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), log2_parts, (u64 *)part_counts);
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+int counter_export_scatter_to(ssq_counter *c, int n_parts, u64 *const *dst_words, uint8_t *const *dst_lens, u64 *const *dst_counts) {
+    int log2_parts = 0;
+    while ((1 << log2_parts) < n_parts) log2_parts++;
+    ssq_ctx *ctx = c->ctx;
+    void *scratch = nullptr;
+    int rc = ctx_scratch(ctx, kMaxParts * sizeof(u64), &scratch);
+    if (rc) return rc;
+    u64 *cursors = (u64 *)scratch;
+    SSQ_CUDA(cudaMemsetAsync(cursors, 0, kMaxParts * sizeof(u64), ctx->stream));      // positions relative to each destination
+    const int64_t cap = (int64_t)1 << c->log2_cap;
+    const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
+    const size_t stage_bytes = (size_t)kThreads * kExportItems * (8 * (W + 1) + 1);
+    const int grid = grid_for(ctx, cap / (kThreads * kExportItems), 3);
+    if (c->klass == SSQ_CLASS_64) {
+        rc = set_max_smem((const void *)export_scatter_kernel<SSQ_CLASS_64>, stage_bytes);
+        if (rc) return rc;
+        export_scatter_kernel<SSQ_CLASS_64><<<grid, kThreads, stage_bytes, ctx->stream>>>(view_of(c), log2_parts, cursors, nullptr, nullptr, nullptr, nullptr, dst_words, dst_lens, dst_counts);
+    } else {
+        rc = set_max_smem((const void *)export_scatter_kernel<SSQ_CLASS_192>, stage_bytes);
+        if (rc) return rc;
+        export_scatter_kernel<SSQ_CLASS_192><<<grid, kThreads, stage_bytes, ctx->stream>>>(view_of(c), log2_parts, cursors, nullptr, nullptr, nullptr, nullptr, dst_words, dst_lens, dst_counts);
+    }
+    SSQ_LAUNCH_CHECK();
+    return SSQ_OK;
+}
+}  // namespace ssq
+
+extern "C" {
 
 int ssq_counter_export_counts(ssq_counter *c, int n_parts, int64_t *part_counts) {
     SSQ_ARG(c != nullptr && part_counts != nullptr, "NULL argument");
