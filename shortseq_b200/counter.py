@@ -225,39 +225,55 @@ def _fill_in_order(dst, groups, add=False):
     hash (the first block); ShortSeqVar keys under their identity, one entry per occurrence, as in the reference."""
     from ._runtime import fastbox
     fb = fastbox()
+    with _NoGC():              # millions of small objects are born here: the cyclic collector would rescan them over and over
+        _fill_in_order_nogc(dst, groups, add, fb)
+
+
+def _fill_in_order_nogc(dst, groups, add, fb):
+    # Everything is put into first-occurrence order BEFORE the objects are created (one argsort + a few numpy takes per
+    # class): the keys are then boxed in their final order and the dict is filled front to back -- objects and dict
+    # entries are touched in allocation order instead of at random (1.26 M keys: fill 0.63 -> 0.36 s).
     objs, counts, firsts, hashes = [], [], [], []
     for klass, w, l, cnt, fi in groups:
+        fi = np.asarray(fi, dtype=np.int64)
+        cnt = np.asarray(cnt, dtype=np.int64)
+        order = np.argsort(fi)              # first-occurrence indices are distinct within a class: no need for a stable sort
+        fi, cnt, l = fi[order], cnt[order], np.asarray(l)[order]
         if klass == CLASS_VAR:
             words, wo = w
-            boxed = [_box(CLASS_VAR, tuple(int(x) for x in words[wo[i]: wo[i + 1]]), int(l[i])) for i in range(len(l))]
+            boxed = [_box(CLASS_VAR, tuple(int(x) for x in words[wo[i]: wo[i + 1]]), int(l[j])) for j, i in enumerate(order.tolist())]
             hs = np.fromiter(map(id, boxed), dtype=np.int64, count=len(boxed))
         else:
-            wv = np.ascontiguousarray(w).view(np.uint64)
+            wv = np.ascontiguousarray(np.asarray(w)[order]).view(np.uint64)
             if fb is not None:
                 boxed = fb.box_many(ShortSeq64 if klass == CLASS_64 else ShortSeq192, wv.tobytes(),
                                     np.ascontiguousarray(l, dtype=np.int64).tobytes(), 1 if klass == CLASS_64 else 3)
             else:
-                boxed = _box_many(klass, w, l)
+                boxed = _box_many(klass, wv.view(np.int64), l)
             hs = (wv if wv.ndim == 1 else wv[:, 0]).view(np.int64).copy()
             hs[hs == -1] = -2
-        objs += boxed
+        objs.append(boxed)
         hashes.append(hs)
-        counts.append(np.asarray(cnt, dtype=np.int64))
-        firsts.append(np.asarray(fi, dtype=np.int64))
+        counts.append(cnt)
+        firsts.append(fi)
     if not objs:
         return
-    order = np.argsort(np.concatenate(firsts), kind="stable")
-    counts = np.concatenate(counts)
+    if len(objs) == 1:                      # one class (the usual case): already in order
+        objs, counts, hashes = objs[0], counts[0], hashes[0]
+        order = np.arange(len(objs), dtype=np.int64)
+    else:                                   # interleave the classes by first occurrence
+        objs = [o for part in objs for o in part]
+        order = np.argsort(np.concatenate(firsts), kind="stable")
+        counts, hashes = np.concatenate(counts), np.concatenate(hashes)
     if fb is not None:
-        fb.fill_counts(dst, objs, counts.tobytes(), np.concatenate(hashes).tobytes(), order.astype(np.int64).tobytes(), bool(add))
+        fb.fill_counts(dst, objs, counts.tobytes(), hashes.tobytes(), order.astype(np.int64).tobytes(), bool(add))
         return
     order, counts = order.tolist(), counts.tolist()
-    with _NoGC():
-        if add:
-            for j in order:
-                dict.__setitem__(dst, objs[j], dict.get(dst, objs[j], 0) + counts[j])
-        else:
-            dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
+    if add:
+        for j in order:
+            dict.__setitem__(dst, objs[j], dict.get(dst, objs[j], 0) + counts[j])
+    else:
+        dict.update(dst, zip([objs[j] for j in order], [counts[j] for j in order]))
 
 
 class ShortSeqCounter(dict):
@@ -328,8 +344,11 @@ def read_and_count_fastq(filename, device=None, chunk_bytes=0):
     self = ShortSeqCounter()
     if data.size == 0:
         return self
-    c64 = DeviceCounter(CLASS_64, expected_unique=0, device=ctx.device)
-    c192 = DeviceCounter(CLASS_192, expected_unique=0, device=ctx.device)
+    # a FASTQ record of an L-nt read takes >= 2 L + 6 bytes: size / 40 bounds the reads of a file of >= 17-nt reads, and a
+    # counter whose bound turns out too small grows (or falls back to the gated mode) by itself
+    bound = int(min(max(data.size // 40, 1 << 16), 1 << 26))
+    c64 = DeviceCounter(CLASS_64, expected_unique=bound, device=ctx.device)
+    c192 = DeviceCounter(CLASS_192, expected_unique=bound, device=ctx.device)
     n_reads, n_longer, first_longer = C.c_int64(), C.c_int64(), C.c_int64()
     rep = _lib.Report()
     h = ctx.bind()

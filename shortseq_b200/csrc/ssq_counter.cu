@@ -1284,6 +1284,8 @@ constexpr size_t kDirectTableBytes = (size_t)48 << 20;
 
 static bool use_deferred(const ssq_counter *c, int64_t n) {
     if (c->expected_unique <= 0) return false;
+    static const bool off = getenv("SSQ_NO_DEFERRED") != nullptr;      // development: direct inserts whatever the table size
+    if (off) return false;
     const size_t table_bytes = ((size_t)1 << c->log2_cap) * slot_bytes(c->klass);
     // worthwhile when the table cannot live in L2 and the pass brings at least ~1 key per 4 slots
     return table_bytes > kDirectTableBytes && n >= ((int64_t)1 << c->log2_cap) / 4;

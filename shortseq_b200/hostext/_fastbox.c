@@ -111,6 +111,7 @@ done:
 /* private but exported CPython API (the reference uses the same calls, counter.pxd:31-37) */
 extern int _PyDict_SetItem_KnownHash(PyObject *mp, PyObject *key, PyObject *item, Py_hash_t hash);
 extern PyObject *_PyDict_GetItem_KnownHash(PyObject *mp, PyObject *key, Py_hash_t hash);
+extern PyObject *_PyDict_NewPresized(Py_ssize_t minused);
 
 static PyObject *fill_counts(PyObject *self, PyObject *args)
 {
@@ -125,6 +126,13 @@ static PyObject *fill_counts(PyObject *self, PyObject *args)
     {
         const int gc_was = PyGC_Disable();
         int failed = 0;
+        /* An empty destination is filled through a dict presized for all m keys (no rehash on the way up) that is then
+         * merged in: merging a clean, freshly built dict into an empty one clones its table. */
+        PyObject *target = d;
+        if (!add && PyDict_GET_SIZE(d) == 0 && m > 1024) {
+            target = _PyDict_NewPresized(m);
+            if (!target) { if (gc_was) PyGC_Enable(); goto done; }
+        }
         for (Py_ssize_t j = 0; j < m && !failed; j++) {
             const int64_t i = ord[j];
             if (i < 0 || i >= n) { PyErr_SetString(PyExc_IndexError, "fill_counts: order out of range"); failed = 1; break; }
@@ -138,8 +146,12 @@ static PyObject *fill_counts(PyObject *self, PyObject *args)
             }
             PyObject *val = PyLong_FromLongLong(c);
             if (!val) { failed = 1; break; }
-            if (_PyDict_SetItem_KnownHash(d, key, val, h) < 0) failed = 1;
+            if (_PyDict_SetItem_KnownHash(target, key, val, h) < 0) failed = 1;
             Py_DECREF(val);
+        }
+        if (target != d) {
+            if (!failed && PyDict_Update(d, target) < 0) failed = 1;
+            Py_DECREF(target);
         }
         if (gc_was) PyGC_Enable();
         if (failed) goto done;
