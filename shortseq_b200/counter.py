@@ -344,16 +344,40 @@ def read_and_count_fastq(filename, device=None, chunk_bytes=0):
     self = ShortSeqCounter()
     if data.size == 0:
         return self
-    # a FASTQ record of an L-nt read takes >= 2 L + 6 bytes: size / 40 bounds the reads of a file of >= 17-nt reads, and a
-    # counter whose bound turns out too small grows (or falls back to the gated mode) by itself
-    bound = int(min(max(data.size // 40, 1 << 16), 1 << 26))
-    c64 = DeviceCounter(CLASS_64, expected_unique=bound, device=ctx.device)
-    c192 = DeviceCounter(CLASS_192, expected_unique=bound, device=ctx.device)
+    # Size ONE counter from the first record (bytes per record -> reads in the file, class of its read): files are
+    # almost always class-homogeneous, and creating / destroying a second large table costs more than counting the file
+    # (cudaFree of a few hundred MB: ~0.1 s).  A counter whose bound turns out too small grows by itself; a read of the
+    # other class makes the call report SSQ_ERR_CLASS, and the file is then counted again with both counters.
+    head = data[: 1 << 16].tobytes()
+    nl, pos_ = [], -1
+    for _ in range(4):
+        pos_ = head.find(b"\n", pos_ + 1)
+        if pos_ < 0:
+            break
+        nl.append(pos_)
+    rec_bytes = nl[3] + 1 if len(nl) == 4 else max(int(data.size), 1)
+    first_len = (nl[1] - nl[0] - 1) if len(nl) >= 2 else 0
+    bound = int(min(max(data.size / rec_bytes * 1.1 + 1024, 1 << 15), 1 << 27))
+    primary = CLASS_64 if first_len <= 32 else CLASS_192
     n_reads, n_longer, first_longer = C.c_int64(), C.c_int64(), C.c_int64()
     rep = _lib.Report()
     h = ctx.bind()
-    _lib.check(_lib.lib().ssq_host_fastq_count(h, c64.handle, c192.handle, data.ctypes.data, int(data.size), int(chunk_bytes), 1,
-                                               C.byref(n_reads), C.byref(n_longer), C.byref(first_longer), C.byref(rep)))
+    counters = {primary: DeviceCounter(primary, expected_unique=bound, device=ctx.device)}
+
+    def run():
+        c64, c192 = counters.get(CLASS_64), counters.get(CLASS_192)
+        _lib.check(_lib.lib().ssq_host_fastq_count(h, None if c64 is None else c64.handle, None if c192 is None else c192.handle, data.ctypes.data,
+                                                   int(data.size), int(chunk_bytes), 1, C.byref(n_reads), C.byref(n_longer),
+                                                   C.byref(first_longer), C.byref(rep)))
+
+    run()
+    if rep.code == _lib.ERR_CLASS:                          # mixed classes: count again with a counter for each
+        other = CLASS_192 if primary == CLASS_64 else CLASS_64
+        counters[primary].clear()
+        counters[other] = DeviceCounter(other, expected_unique=bound, device=ctx.device)
+        run()
+    c64 = counters.get(CLASS_64)
+    c192 = counters.get(CLASS_192)
     bad = rep.first_bad_read if rep.code != _lib.OK else -1
     if n_longer.value and (bad < 0 or first_longer.value < bad):
         read = _fastq_reads_host(data, upto=first_longer.value)[first_longer.value]
@@ -368,7 +392,7 @@ def read_and_count_fastq(filename, device=None, chunk_bytes=0):
         raise Exception(bad_base_message(read))
     groups = []
     for klass, ctr in ((CLASS_64, c64), (CLASS_192, c192)):
-        if len(ctr) == 0:
+        if ctr is None or len(ctr) == 0:
             continue
         keys, counts, first, _ = ctr.export(1, with_first_index=True)
         w, l, _ = keys.to_host()

@@ -96,7 +96,13 @@ static PyObject *box_many(PyObject *self, PyObject *args)
             if (h == -1) h = -2;
             *(PyObject **)((char *)obj + o_packed) = packed;
             *(PyObject **)((char *)obj + o_len) = PyLong_FromLongLong(l[i]);
-            *(PyObject **)((char *)obj + o_hash) = PyLong_FromLongLong(h);
+            if (h >= 0) {                         /* the hash IS the first block: share the int object */
+                PyObject *first = PyTuple_GET_ITEM(packed, 0);
+                Py_INCREF(first);
+                *(PyObject **)((char *)obj + o_hash) = first;
+            } else {
+                *(PyObject **)((char *)obj + o_hash) = PyLong_FromLongLong(h);
+            }
             PyList_SET_ITEM(out, i, obj);
         }
         if (gc_was) PyGC_Enable();
