@@ -306,10 +306,14 @@ __global__ void __launch_bounds__(kThreads) decode_var_kernel(const u64 *words, 
 // busy on a 150-nt read) and chains four dependent global loads per read (length -> output offset -> word offset ->
 // word).  Here a persistent CTA treats the tile's words as ONE flat list -- they are contiguous in the CSR array -- that
 // is loaded coalesced one tile ahead; thread k finds the read of word k with a 5-step search in the tile's 33 word
-// offsets (shared memory, published by warp 0 from offsets it loaded an iteration earlier) and deposits it.
+// offsets and deposits it.  A ninth PRODUCER warp owns the per-tile serial work (offsets loaded two tiles ahead,
+// relative offsets, sanity checks) and publishes each tile's metadata in shared memory behind an mbarrier, running up to
+// kVar2Meta - 1 tiles ahead; the eight consumer warps synchronise among themselves with a named barrier.  (With warp 0
+// publishing between the CTA barriers every tile waited for it: 7 of every 8 stall cycles were barrier waits.)
 constexpr int kVar2Reads = 32;
-constexpr int kVar2Meta = 3;
+constexpr int kVar2Meta = 4;
 constexpr int kVar2WPT = (kVar2Reads * 32) / kThreads;      // words per thread per tile (4)
+constexpr int kVar2Threads = kThreads + 32;                 // consumers + the producer warp
 struct DecVar2Meta {
     int64_t t0, t1, wbase;
     u32 orel[kVar2Reads + 1];   // first output byte of each read relative to t0 (0xFFFFFFFF: outside the tile)
@@ -318,49 +322,75 @@ struct DecVar2Meta {
     int nreads, sane;
 };
 
-__global__ void __launch_bounds__(kThreads) decode_var2_kernel(const u64 *words, const int64_t *word_off,
-                                                               const uint16_t *lens, int64_t n, const int64_t *out_off,
-                                                               uint8_t *out) {
+__global__ void __launch_bounds__(kVar2Threads) decode_var2_kernel(const u64 *words, const int64_t *word_off,
+                                                                   const uint16_t *lens, int64_t n, const int64_t *out_off,
+                                                                   uint8_t *out) {
     __shared__ u32 stream[kVarMaxChunks + 3];
     __shared__ DecVar2Meta meta[kVar2Meta];
+    __shared__ __align__(8) u64 full[kVar2Meta], freed[kVar2Meta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t mis = (int64_t)((uintptr_t)out & 15);
     const int64_t ntiles = (n + kVar2Reads - 1) / kVar2Reads;
     const int64_t stride = gridDim.x;
     const int mytiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + stride - 1) / stride) : 0;
-    for (int c = threadIdx.x; c < kVarMaxChunks + 3; c += kThreads) stream[c] = 0;
+    for (int c = threadIdx.x; c < kVarMaxChunks + 3; c += kVar2Threads) stream[c] = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < kVar2Meta; m++) { mbar_init(smem_addr(&full[m]), 1); mbar_init(smem_addr(&freed[m]), kThreads / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-    int64_t p_o = 0, p_w = 0, p_ol = 0, p_wl = 0;
-    u32 p_len = 0;
-    auto fetch_meta = [&](int j) {                  // warp 0: tile j's offsets into registers
-        if (j >= mytiles) return;
-        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
-        const int nreads = (int)min((int64_t)kVar2Reads, n - first);
-        if (lane < nreads) { p_o = out_off[first + lane]; p_w = word_off[first + lane]; p_len = min((u32)lens[first + lane], 1024u); }
-        if (lane == 0) { p_ol = out_off[first + nreads]; p_wl = word_off[first + nreads]; }
-    };
-    auto publish = [&](int j) {                     // warp 0: registers -> shared metadata of tile j
-        if (j >= mytiles) return;
-        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
-        const int nreads = (int)min((int64_t)kVar2Reads, n - first);
-        DecVar2Meta &m = meta[j % kVar2Meta];
-        const int64_t t0 = __shfl_sync(0xFFFFFFFFu, p_o, 0), wbase = __shfl_sync(0xFFFFFFFFu, p_w, 0);
-        const int64_t t1 = __shfl_sync(0xFFFFFFFFu, p_ol, 0), wend = __shfl_sync(0xFFFFFFFFu, p_wl, 0);
-        if (lane < nreads) {
-            m.orel[lane] = (p_o >= t0 && p_o + p_len <= t1) ? (u32)(p_o - t0) : 0xFFFFFFFFu;
-            m.wrel[lane] = (u32)min(max(p_w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
-            m.len[lane] = p_len;
+    if (warp == kThreads / 32) {
+        // ---- producer warp
+        struct MetaRegs { int64_t p_o = 0, p_w = 0, p_ol = 0, p_wl = 0; u32 p_len = 0; } regs_a, regs_b;
+        auto fetch_meta = [&](int j, MetaRegs &R) {
+            if (j >= mytiles) return;
+            const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+            const int nreads = (int)min((int64_t)kVar2Reads, n - first);
+            if (lane < nreads) { R.p_o = out_off[first + lane]; R.p_w = word_off[first + lane]; R.p_len = min((u32)lens[first + lane], 1024u); }
+            if (lane == 0) { R.p_ol = out_off[first + nreads]; R.p_wl = word_off[first + nreads]; }
+        };
+        auto publish = [&](int j, const MetaRegs &R) {
+            const int ms = j % kVar2Meta;
+            if (j >= kVar2Meta) mbar_wait(smem_addr(&freed[ms]), (u32)(j / kVar2Meta - 1) & 1u);     // tile j - kVar2Meta is done with the slot
+            const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+            const int nreads = (int)min((int64_t)kVar2Reads, n - first);
+            DecVar2Meta &m = meta[ms];
+            const int64_t t0 = __shfl_sync(0xFFFFFFFFu, R.p_o, 0), wbase = __shfl_sync(0xFFFFFFFFu, R.p_w, 0);
+            const int64_t t1 = __shfl_sync(0xFFFFFFFFu, R.p_ol, 0), wend = __shfl_sync(0xFFFFFFFFu, R.p_wl, 0);
+            if (lane < nreads) {
+                m.orel[lane] = (R.p_o >= t0 && R.p_o + R.p_len <= t1) ? (u32)(R.p_o - t0) : 0xFFFFFFFFu;
+                m.wrel[lane] = (u32)min(max(R.p_w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+                m.len[lane] = R.p_len;
+            }
+            if (lane == 0) {
+                m.wrel[nreads] = (u32)min(max(wend - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+                m.t0 = t0; m.t1 = t1; m.wbase = wbase; m.nreads = nreads;
+                m.sane = t1 >= t0 && t1 - t0 <= (int64_t)kVar2Reads * 1024;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&full[ms]));
+        };
+        fetch_meta(0, regs_a);
+        fetch_meta(1, regs_b);
+        for (int j = 0; j < mytiles; j += 2) {
+            publish(j, regs_a);
+            fetch_meta(j + 2, regs_a);
+            if (j + 1 < mytiles) {
+                publish(j + 1, regs_b);
+                fetch_meta(j + 3, regs_b);
+            }
         }
-        if (lane == 0) {
-            m.wrel[nreads] = (u32)min(max(wend - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
-            m.t0 = t0; m.t1 = t1; m.wbase = wbase; m.nreads = nreads;
-            m.sane = t1 >= t0 && t1 - t0 <= (int64_t)kVar2Reads * 1024;
-        }
-    };
-    auto load_words = [&](int j, u64 (&w)[kVar2WPT]) {   // everyone: the words of tile j (its metadata is published)
+        return;
+    }
+
+    // ---- consumer warps
+    auto load_words = [&](int j, u64 (&w)[kVar2WPT]) {   // the words of tile j, once its metadata is published
 #pragma unroll
         for (int i = 0; i < kVar2WPT; i++) w[i] = 0;
         if (j >= mytiles) return;
+        mbar_wait(smem_addr(&full[j % kVar2Meta]), (u32)(j / kVar2Meta) & 1u);
         const DecVar2Meta &m = meta[j % kVar2Meta];
         const u32 tw = m.wrel[m.nreads];
         const u64 *src = words + m.wbase;
@@ -370,8 +400,6 @@ __global__ void __launch_bounds__(kThreads) decode_var2_kernel(const u64 *words,
             if (k < tw) w[i] = src[k];
         }
     };
-    if (warp == 0) { fetch_meta(0); publish(0); fetch_meta(1); publish(1); fetch_meta(2); }
-    __syncthreads();
     u64 cw[kVar2WPT];
     load_words(0, cw);
     for (int j = 0; j < mytiles; j++) {
@@ -402,12 +430,13 @@ __global__ void __launch_bounds__(kThreads) decode_var2_kernel(const u64 *words,
                 }
             }
         }
-        __syncthreads();
-        if (warp == 0) { publish(j + 2); fetch_meta(j + 3); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&freed[j % kVar2Meta]));     // t0 / t1 / a0 are in registers: the slot is free
+        named_bar_sync(1, kThreads);                                       // every deposit of the tile has landed
         u64 nw[kVar2WPT];
-        load_words(j + 1, nw);                                 // in flight during the store phase
+        load_words(j + 1, nw);                                             // in flight during the store phase
         if (sane) store_tile<kThreads>(out, a0, t0, t1, stream, 3);
-        __syncthreads();
+        named_bar_sync(1, kThreads);                                       // the stream is clean again
 #pragma unroll
         for (int i = 0; i < kVar2WPT; i++) cw[i] = nw[i];
     }
@@ -655,10 +684,10 @@ int ssq_decodevar(ssq_ctx *ctx, const uint64_t *words, const int64_t *word_off, 
     DeviceGuard g(ctx->device);
     static const bool v1 = getenv("SSQ_VAR_V1") != nullptr;      // development: the first version of the kernel
     int per_sm = 8;
-    if (!v1 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_var2_kernel, kThreads, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
+    if (!v1 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_var2_kernel, kVar2Threads, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
     int grid = grid_for(ctx, (n + kVarTileReads - 1) / kVarTileReads, per_sm);      // the second version is persistent: exactly one wave
     if (v1) decode_var_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
-    else decode_var2_kernel<<<grid, kThreads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
+    else decode_var2_kernel<<<grid, kVar2Threads, 0, ctx->stream>>>((const u64 *)words, word_off, lens, n, out_offsets, ascii_out);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

@@ -143,6 +143,16 @@ __device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
+// named barriers for a subset of the CTA's warps (the consumer warps of a warp-specialised kernel)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)pred) : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ uint4 lds_v4(u32 addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");

@@ -778,118 +778,133 @@ struct Var2Smem {
     uint8_t raw[kVar2Stages][kVar2RawBytes];
     u32 codes[kVar2Codes][kVar2MaxChunks + 4];
     Var2Meta meta[kVar2Meta];
-    u64 bar[kVar2Stages];
+    u64 full[kVar2Stages];       // producer -> consumers: tile published (metadata written, bytes landed)
+    u64 enc_done[kVar2Stages];   // consumers -> producer: raw[s] has been encoded, the stage may be refilled
+    u64 ext_done[kVar2Meta];     // consumers -> producer: the tile of this metadata slot has been extracted
 };
 
-__global__ void __launch_bounds__(kPackThreads, SSQ_VAR2_CTAS) pack_var2_kernel(PackArgs a) {
+// 8 consumer warps + 1 producer warp.  The producer owns everything that is per tile and serial -- the offsets (loaded two
+// tiles ahead), the tile geometry, the lengths / length errors, the metadata slot, arming the mbarrier and issuing the
+// bulk copy -- and runs up to kVar2Stages tiles ahead of the consumers, which only wait on the stage's `full` barrier.
+// In the first bulk-copy version warp 0 did that work between the consumers' barriers: ~150 instructions on top of a
+// warp's ~175 per tile, so every tile waited for warp 0 (ncu: 31 % of the stall samples at that barrier).
+constexpr int kVar2Consumers = kPackThreads;               // 256 threads extract
+constexpr int kVar2Threads = kVar2Consumers + 32;          // + the producer warp
+
+__global__ void __launch_bounds__(kVar2Threads, SSQ_VAR2_CTAS) pack_var2_kernel(PackArgs a) {
     extern __shared__ __align__(128) uint8_t var2_dyn[];
     Var2Smem &sm = *reinterpret_cast<Var2Smem *>(var2_dyn);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ntiles = (a.n + kVar2Reads - 1) / kVar2Reads;
     const int64_t stride = gridDim.x;
     const int mytiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + stride - 1) / stride) : 0;
-    const u64 drop = l2_policy_evict_first();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kVar2Stages; s++) mbar_init(smem_addr(&sm.bar[s]), 1);
+        for (int s = 0; s < kVar2Stages; s++) { mbar_init(smem_addr(&sm.full[s]), 1); mbar_init(smem_addr(&sm.enc_done[s]), kVar2Consumers / 32); }
+#pragma unroll
+        for (int m = 0; m < kVar2Meta; m++) mbar_init(smem_addr(&sm.ext_done[m]), kVar2Consumers / 32);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // ---- producer state (warp 0): the offsets of the next two tiles to issue, loaded two iterations ahead (the tile
-    // loop is unrolled by two, one register set each) so that issuing a copy never waits for an offsets load.
-    // Measured on the 150/300/1000-nt mix: 32-read tiles 1.63 ms per 1e7 reads, 24-read 1.85, 16-read 2.08, 8-read 2.8 --
-    // per-tile costs (two barriers, the ragged last round of the 256-thread loops over ~730 chunks / ~365 words) favour
-    // the largest tile that still leaves three CTAs per SM; a second code buffer (one barrier per tile, two CTAs per SM)
-    // and a third stage both measured slower.
-    struct MetaRegs { int64_t p_off = 0, p_off_last = 0, p_woff = 0, p_woff_last = 0; } regs_a, regs_b;
-    auto fetch_meta = [&](int j, MetaRegs &R) {     // warp 0: offsets / word offsets of this CTA's j-th tile into registers
-        int64_t &p_off = R.p_off, &p_off_last = R.p_off_last, &p_woff = R.p_woff, &p_woff_last = R.p_woff_last;
-        if (j >= mytiles) return;
-        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
-        const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
-        if (lane <= nreads) { p_off = a.offsets[first + lane]; p_woff = a.word_off[first + lane]; }
-        if (lane == 0) { p_off_last = a.offsets[first + nreads]; p_woff_last = a.word_off[first + nreads]; }
-    };
-    auto issue = [&](int j, const MetaRegs &R) {    // warp 0: publish tile j's metadata, start its copy; R holds its offsets
-        const int64_t p_off = R.p_off, p_off_last = R.p_off_last, p_woff = R.p_woff, p_woff_last = R.p_woff_last;
-        if (j >= mytiles) return;
-        const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
-        const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
-        Var2Meta &m = sm.meta[j % kVar2Meta];
-        const int64_t t0 = __shfl_sync(0xFFFFFFFFu, p_off, 0), wbase = __shfl_sync(0xFFFFFFFFu, p_woff, 0);
-        const int64_t t1 = __shfl_sync(0xFFFFFFFFu, p_off_last, 0), wend = __shfl_sync(0xFFFFFFFFu, p_woff_last, 0);
-        int64_t nxt = __shfl_down_sync(0xFFFFFFFFu, p_off, 1);
-        if (lane == nreads - 1) nxt = t1;
-        const bool tile_ok = t0 >= a.lo && t1 >= t0 && t1 <= a.hi && (t1 - t0) <= (int64_t)kVar2Reads * 1024 &&
-                             wend >= wbase && wend - wbase <= (int64_t)kVar2Reads * 32;
-        if (lane < nreads) {
-            const int64_t len = nxt - p_off;
-            const bool len_ok = len >= 97 && len <= 1024 && p_off >= t0 && nxt <= t1;
-            if (len < 97 || len > 1024) report_len(a.rep, len, (u64)(a.index_base + first + lane));
-            ((uint16_t *)a.lens)[first + lane] = (tile_ok && len_ok) ? (uint16_t)len : 0;
-        }
-        if (lane <= nreads) {
-            const int64_t o = lane == nreads ? t1 : p_off, w = lane == nreads ? wend : p_woff;
-            m.srel[lane] = (o >= t0 && o <= t1) ? (u32)(o - t0) : 0xFFFFFFFFu;
-            m.wrel[lane] = (u32)min(max(w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
-        }
-        if (lane == 0) {
-            if (nreads == kVar2Reads) {             // entry 32 belongs to lane 0 (a warp has 32 lanes, a tile 33 boundaries)
+    if (warp == kVar2Consumers / 32) {
+        // =========================================== producer warp ===========================================
+        const u64 drop = l2_policy_evict_first();
+        struct MetaRegs { int64_t p_off = 0, p_off_last = 0, p_woff = 0, p_woff_last = 0; } regs_a, regs_b;
+        auto fetch_meta = [&](int j, MetaRegs &R) {     // offsets / word offsets of this CTA's j-th tile into registers
+            if (j >= mytiles) return;
+            const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+            const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
+            if (lane <= nreads) { R.p_off = a.offsets[first + lane]; R.p_woff = a.word_off[first + lane]; }
+            if (lane == 0) { R.p_off_last = a.offsets[first + nreads]; R.p_woff_last = a.word_off[first + nreads]; }
+        };
+        auto issue = [&](int j, const MetaRegs &R) {    // publish tile j (its offsets are in R) and start its copy
+            const int64_t p_off = R.p_off, p_off_last = R.p_off_last, p_woff = R.p_woff, p_woff_last = R.p_woff_last;
+            const int s = j % kVar2Stages, ms = j % kVar2Meta;
+            // the stage was last filled for tile j - kVar2Stages, the metadata slot last used by tile j - kVar2Meta
+            if (j >= kVar2Stages) mbar_wait(smem_addr(&sm.enc_done[s]), (u32)(j / kVar2Stages - 1) & 1u);
+            if (j >= kVar2Meta) mbar_wait(smem_addr(&sm.ext_done[ms]), (u32)(j / kVar2Meta - 1) & 1u);
+            const int64_t first = ((int64_t)blockIdx.x + (int64_t)j * stride) * kVar2Reads;
+            const int nreads = (int)min((int64_t)kVar2Reads, a.n - first);
+            Var2Meta &m = sm.meta[ms];
+            const int64_t t0 = __shfl_sync(0xFFFFFFFFu, p_off, 0), wbase = __shfl_sync(0xFFFFFFFFu, p_woff, 0);
+            const int64_t t1 = __shfl_sync(0xFFFFFFFFu, p_off_last, 0), wend = __shfl_sync(0xFFFFFFFFu, p_woff_last, 0);
+            int64_t nxt = __shfl_down_sync(0xFFFFFFFFu, p_off, 1);
+            if (lane == nreads - 1) nxt = t1;
+            const bool tile_ok = t0 >= a.lo && t1 >= t0 && t1 <= a.hi && (t1 - t0) <= (int64_t)kVar2Reads * 1024 &&
+                                 wend >= wbase && wend - wbase <= (int64_t)kVar2Reads * 32;
+            if (lane < nreads) {
+                const int64_t len = nxt - p_off;
+                const bool len_ok = len >= 97 && len <= 1024 && p_off >= t0 && nxt <= t1;
+                if (len < 97 || len > 1024) report_len(a.rep, len, (u64)(a.index_base + first + lane));
+                ((uint16_t *)a.lens)[first + lane] = (tile_ok && len_ok) ? (uint16_t)len : 0;
+            }
+            if (lane <= nreads) {
+                const int64_t o = lane == nreads ? t1 : p_off, w = lane == nreads ? wend : p_woff;
+                m.srel[lane] = (o >= t0 && o <= t1) ? (u32)(o - t0) : 0xFFFFFFFFu;
+                m.wrel[lane] = (u32)min(max(w - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
+            }
+            if (lane == 0 && nreads == kVar2Reads) {    // entry 32 belongs to lane 0 (a warp has 32 lanes, a tile 33 boundaries)
                 m.srel[nreads] = (u32)(t1 - t0);
                 m.wrel[nreads] = (u32)min(max(wend - wbase, (int64_t)0), (int64_t)kVar2Reads * 32);
             }
-            int mode = 0;
-            TileGeom g = tile_geom(a.ascii, a.lo, a.hi, t0, tile_ok ? (int)(t1 - t0) : 0);
-            if (tile_ok) mode = g.interior ? 1 : 2;
-            else if (t0 < a.lo || t1 > a.hi || t1 < t0) atomicMin(&a.rep->first_bad_len, (u64)(a.index_base + first));
-            m.t0 = t0; m.wbase = wbase; m.nreads = nreads; m.nchunks = g.nchunks; m.lead = g.lead; m.mode = mode; m.a0 = g.a0;
-            if (mode == 1 && g.nchunks > 0) {
-                const u32 bar = smem_addr(&sm.bar[j % kVar2Stages]);
-                mbar_expect_tx(bar, 16u * (u32)g.nchunks);
-                bulk_g2s(smem_addr(sm.raw[j % kVar2Stages]), g.src, 16u * (u32)g.nchunks, bar, drop);
-            } else if (mode == 1) {
-                m.mode = 2;                         // empty byte range: nothing to copy, nothing to wait for
+            __syncwarp();                               // every lane's metadata stores precede lane 0's arrive (release)
+            if (lane == 0) {
+                int mode = 0;
+                TileGeom g = tile_geom(a.ascii, a.lo, a.hi, t0, tile_ok ? (int)(t1 - t0) : 0);
+                if (tile_ok) mode = (g.interior && g.nchunks > 0) ? 1 : 2;
+                else if (t0 < a.lo || t1 > a.hi || t1 < t0) atomicMin(&a.rep->first_bad_len, (u64)(a.index_base + first));
+                m.t0 = t0; m.wbase = wbase; m.nreads = nreads; m.nchunks = g.nchunks; m.lead = g.lead; m.mode = mode; m.a0 = g.a0;
+                const u32 bar = smem_addr(&sm.full[s]);
+                if (mode == 1) {
+                    mbar_expect_tx(bar, 16u * (u32)g.nchunks);
+                    bulk_g2s(smem_addr(sm.raw[s]), g.src, 16u * (u32)g.nchunks, bar, drop);
+                } else {
+                    mbar_arrive(bar);                   // nothing travels: the tile is complete as published
+                }
+            }
+            __syncwarp();
+        };
+        fetch_meta(0, regs_a);
+        fetch_meta(1, regs_b);
+        for (int j = 0; j < mytiles; j += 2) {
+            issue(j, regs_a);
+            fetch_meta(j + 2, regs_a);
+            if (j + 1 < mytiles) {
+                issue(j + 1, regs_b);
+                fetch_meta(j + 3, regs_b);
             }
         }
-    };
-    if (warp == 0) {
-        for (int j = 0; j < kVar2Stages; j++) { fetch_meta(j, regs_a); issue(j, regs_a); }
-        fetch_meta(kVar2Stages, regs_a);
-        fetch_meta(kVar2Stages + 1, regs_b);
+        return;
     }
-    __syncthreads();
 
-    u32 phase = 0;                                   // bit s: parity of stage s's next completion
-    auto tile_body = [&](int j, MetaRegs &R) {      // R: offsets of tile j + kVar2Stages (refilled for tile j + kVar2Stages + 2)
-        if (j >= mytiles) return;
-        const int s = j % kVar2Stages;
+    // ================================================ consumer warps ================================================
+    for (int j = 0; j < mytiles; j++) {
+        const int s = j % kVar2Stages, ms = j % kVar2Meta;
         u32 *const codes = sm.codes[j % kVar2Codes];
-        const Var2Meta &m = sm.meta[j % kVar2Meta];
+        mbar_wait(smem_addr(&sm.full[s]), (u32)(j / kVar2Stages) & 1u);
+        const Var2Meta &m = sm.meta[ms];
         const int mode = m.mode, nchunks = m.nchunks, lead = m.lead, nreads = m.nreads;
         const int64_t t0 = m.t0;
         u32 bad = 0;
         if (mode == 1) {
-            mbar_wait(smem_addr(&sm.bar[s]), (phase >> s) & 1u);
-            phase ^= 1u << s;
             const u32 raw = smem_addr(sm.raw[s]);
-            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) codes[c] = encode16(lds_v4(raw + 16 * c), bad);
+            for (int c = threadIdx.x; c < nchunks; c += kVar2Consumers) codes[c] = encode16(lds_v4(raw + 16 * c), bad);
         } else if (mode == 2) {
-            for (int c = threadIdx.x; c < nchunks; c += kPackThreads) {
+            for (int c = threadIdx.x; c < nchunks; c += kVar2Consumers) {
                 const int64_t idx = m.a0 + 16 * (int64_t)c;
                 const uint4 x = (idx >= a.lo && idx + 16 <= a.hi) ? ld_stream_v4(a.ascii + idx) : load_chunk_guarded(a.ascii, a.lo, a.hi, idx);
                 codes[c] = encode16(x, bad);
             }
         }
         if (threadIdx.x < 4) codes[nchunks + threadIdx.x] = 0;
-        // The only barrier of a tile: codes[j & 1] complete, raw[s] consumed.  Every thread has also finished extracting
-        // tile j - 1 (program order), so codes[(j + 1) & 1] and the metadata slot of tile j - 1 may be rewritten.
-        const int tile_bad = __syncthreads_or(bad != 0);
-        if (warp == 0) { issue(j + kVar2Stages, R); fetch_meta(j + kVar2Stages + 2, R); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&sm.enc_done[s]));        // this warp no longer reads raw[s]
+        const bool tile_bad = named_bar_or(1, kVar2Consumers, bad != 0);    // codes complete
         if (mode != 0) {
             const u32 tw = m.wrel[nreads];
             u64 *wdst = a.words + m.wbase;
-            for (u32 k = threadIdx.x; k < tw; k += kPackThreads) {
+            for (u32 k = threadIdx.x; k < tw; k += kVar2Consumers) {
                 int lo_ = 0, hi_ = nreads;                    // wrel[lo_] <= k < wrel[hi_]
 #pragma unroll
                 for (int it = 0; it < kVar2Log2Reads; it++) {
@@ -902,7 +917,7 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_VAR2_CTAS) pack_var2_kernel(
                 wdst[k] = ok ? keep_bits(extract64(codes, 2 * ((int)r0 + lead) + 64 * jw), 2 * len - 64 * jw) : 0ull;
             }
             if (tile_bad) {                                   // some byte near the tile is invalid: exact re-check, warp per read
-                for (int r = warp; r < nreads; r += kPackThreads / 32) {
+                for (int r = warp; r < nreads; r += kVar2Consumers / 32) {
                     const u32 r0 = m.srel[r], r1 = m.srel[r + 1];
                     if (r0 == 0xFFFFFFFFu || r1 == 0xFFFFFFFFu || r1 < r0 || r1 - r0 > 1024 || r1 - r0 < 97) continue;
                     bool b = false;
@@ -912,11 +927,9 @@ __global__ void __launch_bounds__(kPackThreads, SSQ_VAR2_CTAS) pack_var2_kernel(
                 }
             }
         }
-        if (kVar2Codes == 1) __syncthreads();          // single code buffer: the next tile's encode rewrites it
-    };
-    for (int j = 0; j < mytiles; j += 2) {
-        tile_body(j, regs_a);
-        tile_body(j + 1, regs_b);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&sm.ext_done[ms]));       // this warp no longer reads the tile's metadata
+        if (kVar2Codes == 1) named_bar_sync(1, kVar2Consumers);        // single code buffer: the next tile's encode rewrites it
     }
 }
 
@@ -1090,8 +1103,8 @@ int ssq_packvar(ssq_ctx *ctx, const uint8_t *ascii, int64_t ascii_bytes, const i
     SSQ_CUDA(cudaFuncSetAttribute(pack_var2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Var2Smem)));
     SSQ_CUDA(cudaFuncSetAttribute(pack_var2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_var2_kernel, kPackThreads, sizeof(Var2Smem)) != cudaSuccess || per_sm < 1) per_sm = 2;
-    pack_var2_kernel<<<grid_for(ctx, (n + kVar2Reads - 1) / kVar2Reads, per_sm), kPackThreads, sizeof(Var2Smem), ctx->stream>>>(a);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_var2_kernel, kVar2Threads, sizeof(Var2Smem)) != cudaSuccess || per_sm < 1) per_sm = 2;
+    pack_var2_kernel<<<grid_for(ctx, (n + kVar2Reads - 1) / kVar2Reads, per_sm), kVar2Threads, sizeof(Var2Smem), ctx->stream>>>(a);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }
