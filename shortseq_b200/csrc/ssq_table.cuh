@@ -86,8 +86,11 @@ struct TableView {
 
 // Regions of 2^12 slots for tables of 2^18 .. 2^28 slots (64 .. 65536 regions); 1/64 of a smaller table; larger
 // regions beyond 2^28 slots so that a level-1 partition never holds more than 256 of them.
+#ifndef SSQ_REGION_SHIFT
+#define SSQ_REGION_SHIFT 16      /* development: 15 / 14 -> regions of 2^13 / 2^14 slots at 2^28 slots */
+#endif
 __host__ __device__ __forceinline__ int region_bits_for(int log2_cap) {
-    return log2_cap < 18 ? log2_cap - 6 : (log2_cap <= 28 ? 12 : log2_cap - 16);
+    return log2_cap < 18 ? log2_cap - 6 : (log2_cap <= 12 + SSQ_REGION_SHIFT ? 12 : log2_cap - SSQ_REGION_SHIFT);
 }
 
 // ---- ShortSeq64 ------------------------------------------------------------
