@@ -127,6 +127,35 @@ def test_last_char_bad_every_var_length(sq):
         assert rep.code == _lib.ERR_BAD_BASE and rep.first_bad_read == i
 
 
+def test_var_bad_reads_spread_over_tiles(sq):
+    """ShortSeqVar pack finds the failing reads from a shared-memory list of invalid chunks: bad bytes at the first / last
+    byte of a read (they share 16-byte chunks and 32-read tiles with their neighbours), many bad reads at once, and more
+    invalid chunks in one tile than the list holds (the kernel then re-reads the tile's reads): the report is always the
+    LOWEST failing read."""
+    from shortseq_b200 import _lib
+    from shortseq_b200.batch import ReadBatch, _pack_raw
+    rng = np.random.default_rng(23)
+    reads = rand_reads(rng, 4000, 97, 700)
+
+    def first_bad(rs):
+        _, rep = _pack_raw(ReadBatch.make(rs), 2)
+        assert rep.code == _lib.ERR_BAD_BASE
+        return int(rep.first_bad_read)
+
+    for positions in ([(3999, -1)], [(3100, 0)], [(31, -1), (32, 0)], [(2000, 5), (64, 0), (63, -1), (3000, 7)],
+                      [(i, int(rng.integers(0, 97))) for i in range(500, 4000, 37)]):
+        rs = list(reads)
+        for i, at in positions:
+            r = bytearray(rs[i]); r[at] = ord("N"); rs[i] = bytes(r)
+        assert first_bad(rs) == min(i for i, _ in positions)
+    rs = list(reads)                                   # every read of tiles 40..41 bad in many places: list overflow
+    for i in range(40 * 32, 42 * 32):
+        r = bytearray(rs[i]); r[::9] = b"N" * len(r[::9]); rs[i] = bytes(r)
+    assert first_bad(rs) == 40 * 32
+    rs[7] = rs[7][:50] + b"n" + rs[7][51:]
+    assert first_bad(rs) == 7
+
+
 def test_length_errors(sq):
     with pytest.raises(Exception, match="longer than 1024 bases"):
         sq.pack(b"A" * 1025)
