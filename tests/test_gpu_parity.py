@@ -528,6 +528,56 @@ def test_counter_deferred_192(sq, oracle, skew):
     assert counter_dict(kw, kl, counts.cpu().numpy()) == {k: 2 * v for k, v in expect.items()}
 
 
+@pytest.mark.parametrize("L,shift,variant", [(75, 0, "clean"), (33, 5, "clean"), (96, 11, "clean"), (64, 0, "clean"),
+                                             (75, 3, "ragged"), (75, 0, "bad")])
+def test_counter_deferred_192_uniform_length(sq, oracle, L, shift, variant):
+    """ShortSeq192 batches of one read length through the deferred path (the C3 shape), at every alignment class of the
+    tile geometry.  shift: the ASCII buffer starts `shift` bytes off a 16-byte boundary.  ragged: two pairs of reads trade
+    one base (74 / 76 nt) so that the batch still holds L n bytes but is not uniform.  bad: invalid bases in three reads;
+    the lowest one is reported and nothing else changes.  (A fixed-length fast-path kernel that only checked the offsets
+    against the progression was built against this test and measured 2 % faster than the general kernel: dropped.)"""
+    import torch
+    from shortseq_b200 import _lib
+    from shortseq_b200.batch import ReadBatch
+    n, u = 1_300_000 + 77, 600_000
+    b0 = sq.synth_reads(n, u, L, L, seed=0x5EED0077 + L)
+    buf, off = b0.ascii.cpu().numpy().copy(), b0.offsets.cpu().numpy().copy()
+    if variant == "ragged":
+        for i in (1000, 700_001):
+            off[i + 1] -= 1            # read i loses its last base to read i + 1
+    bad_reads = []
+    if variant == "bad":
+        bad_reads = [900_000, 412_345, 1_299_999]
+        for i in bad_reads:
+            buf[off[i] + (i % L)] = ord("N")
+    dev = torch.empty(buf.size + 16, dtype=torch.uint8, device=b0.ascii.device)
+    dev[shift: shift + buf.size] = torch.from_numpy(buf).to(dev.device)
+    b = ReadBatch.make(dev[shift: shift + buf.size], torch.from_numpy(off).to(dev.device))
+    ctr = sq.DeviceCounter(1, expected_unique=1_000_000)       # 2^21 slots x 32 B = 64 MB: deferred counting
+    arr = ctr.pack_count(b, check=False)
+    rep = ctr.ctx.sync()
+    if variant == "bad":
+        assert rep.code == _lib.ERR_BAD_BASE and rep.first_bad_read == min(bad_reads)
+        good = np.ones(n, dtype=bool)
+        good[bad_reads] = False
+    else:
+        assert rep.code == _lib.OK
+        good = np.ones(n, dtype=bool)
+    clean = buf.copy()
+    for i in bad_reads:
+        clean[off[i] + (i % L)] = ord("A")                     # the oracle packs a clean copy; bad reads are left out of the counts
+    ow, ol, _ = oracle.pack_batch(1, clean, off)
+    w, l, _ = arr.to_host()
+    assert np.array_equal(l, ol)
+    assert np.array_equal(w[good], ow[good])
+    uw, ul, uc, _ = oracle.count(ow[good], ol[good], 3)
+    expect = counter_dict(uw, ul, uc)
+    keys, counts, _, _ = ctr.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(ctr) == len(expect)
+    assert counter_dict(kw, kl, counts.cpu().numpy()) == expect
+
+
 @pytest.mark.parametrize("owner_unique", [400_000, 250_000])
 def test_counter_merge_regions(sq, oracle, owner_unique):
     """The owner side of the multi-GPU merge on one GPU: P sender tables export one owner's share (tuples + region
