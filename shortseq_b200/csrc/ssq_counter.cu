@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 3) merge_regions_kernel(TableView t,
                 if (lv[u] == 0xFFFFFFFFu) continue;
                 const u32 len = lv[u];
                 const u64 add = av[u];
-                const u64 h2 = rotl64(mix64(wv[u]), t.rot);
+                const u64 h2 = table_hash64(wv[u], t.rot);
                 if (len > 32 || (u32)((h2 >> off_shift) >> t.log2_region) != region) { ++bad; continue; }   // not this region's tuple
                 const u64 key = key64_of(h2, len);
                 u32 off = (u32)(h2 >> off_shift) & rmask;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t
                 atomicMin(&t.rep->first_bad_len, (u64)(index_base + tile * tile_keys + k * kThreads + threadIdx.x));
                 continue;
             }
-            const u64 h2 = rotl64(mix64(word[k]), t.rot);
+            const u64 h2 = table_hash64(word[k], t.rot);
             const u64 key = key64_of(h2, len[k]);
             if (!stage_key(stg, (u32)(h2 >> 56), key)) {
                 bool is_new = false;
@@ -863,7 +863,7 @@ __device__ __forceinline__ Tuple read_slot(const TableView &t, u64 s, int log2_p
         if (key == 0) return r;
         u64 h2 = slot64_h2(t, s, key, r.len);
         h = rotr64(h2, t.rot);
-        r.w0 = unmix64(h);
+        r.w0 = unhash64(h);
         r.count = t.slots[2 * s + 1];
     } else {
         u64 meta = t.slots[4 * s];
@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__(kThreads) export_regions_kernel(TableView t, c
                 const u64 s = slot0 + tile0 + k * kThreads + threadIdx.x;
                 u32 len;
                 const u64 h2 = slot64_h2(t, s, key[k], len);
-                s_word[at + ph8] = unmix64(rotr64(h2, t.rot));
+                s_word[at + ph8] = unhash64(rotr64(h2, t.rot));
                 s_count[at + phc] = cnt[k];
                 s_len[at + ph1] = (uint8_t)len;
                 if (d.first_idx) d.first_idx[o + at] = (int64_t)(t.first_idx ? t.first_idx[s] : kNoIndex);

@@ -40,6 +40,24 @@ __host__ __device__ __forceinline__ u64 unmix64(u64 x) {
 __host__ __device__ __forceinline__ u64 rotl64(u64 x, int r) { return r ? (x << r) | (x >> (64 - r)) : x; }
 __host__ __device__ __forceinline__ u64 rotr64(u64 x, int r) { return r ? (x >> r) | (x << (64 - r)) : x; }
 
+// Table hash of a ShortSeq64 key: a BIJECTION on 64-bit words (the table stores the hash and recovers the word on export)
+// whose top bits -- partition, region and home slot are the top bits of the hash -- depend on every input bit: the high
+// word is folded into the low word (so that reads differing only in their last bases do not differ only in the top hash
+// bits), then one multiply by an odd constant.  Five instructions; the splitmix64 finaliser it replaces (two 64-bit
+// multiplies, three xor-shifts) was 9 % of the fused pack kernel's instructions, and the variable rotate behind it
+// (rot = 0 on one GPU) another 4 %: table_hash64 takes the rotation as two funnel shifts.
+constexpr u64 kHashMul = 0x9E3779B97F4A7C15ull, kHashMulInv = 0xF1DE83E19937733Dull;   // kHashMul * kHashMulInv == 1 (mod 2^64)
+__host__ __device__ __forceinline__ u64 hash64(u64 x) { return (x ^ (x >> 32)) * kHashMul; }
+__host__ __device__ __forceinline__ u64 unhash64(u64 h) { const u64 y = h * kHashMulInv; return y ^ (y >> 32); }
+// rotl(hash64(word), rot), rot in 0..63 and uniform over the launch
+__device__ __forceinline__ u64 table_hash64(u64 word, int rot) {
+    const u64 h = hash64(word);
+    u32 lo = (u32)h, hi = (u32)(h >> 32);
+    if (rot & 32) { const u32 t = lo; lo = hi; hi = t; }
+    const u32 r = (u32)rot & 31u;
+    return ((u64)__funnelshift_l(lo, hi, r) << 32) | __funnelshift_l(hi, lo, r);
+}
+
 // Slot hash of a 3-word key (ShortSeq192).  Not a bijection; the key is stored verbatim.  The three words are folded
 // with odd rotations (a 2-bit code never lines up with itself) and one multiply before a single splitmix round: the
 // first version ran three rounds (six 64-bit multiplies) and was 12 % of the fused pack+scatter kernel's instructions.

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
                     }
                     if constexpr (MODE == kModeScatter) {
                         if (ok2[q]) {
-                            const u64 h2 = rotl64(mix64(w2[q]), t.rot);
+                            const u64 h2 = table_hash64(w2[q], t.rot);
                             const u64 key = key64_of(h2, 32u);
                             if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
                         }
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
                     if (ok) {
                         // stage the table key / record for its hash partition; a full staging ring: count it right away
                         if constexpr (KLASS == SSQ_CLASS_64) {
-                            const u64 h2 = rotl64(mix64(w[0]), t.rot);
+                            const u64 h2 = table_hash64(w[0], t.rot);
                             const u64 key = key64_of(h2, (u32)len);
                             if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
                         } else {
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) pack32_kernel
                 bool staged[2];
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
-                    h2[q] = rotl64(mix64(w2[q]), t.rot);
+                    h2[q] = table_hash64(w2[q], t.rot);
                     key[q] = key64_of(h2[q], 32u);
                     part[q] = (u32)(h2[q] >> 56);
                 }
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) pack32_kernel
                     my_new += is_new ? 1u : 0u;
                 }
                 if constexpr (MODE == kModeScatter) {
-                    const u64 h2 = rotl64(mix64(word), t.rot);
+                    const u64 h2 = table_hash64(word, t.rot);
                     const u64 key = key64_of(h2, len);
                     if (!stage_key(stg, (u32)(h2 >> 56), key)) insert64_slow(t, h2, key, &s_unstaged_new);
                 }

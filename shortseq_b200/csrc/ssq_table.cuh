@@ -4,7 +4,7 @@
 // key = (length, words), value = multiplicity.
 //
 // ShortSeq64 table (16-byte slots {key, count}):
-//   h2  = rotl(mix64(word), rot)        mix64 is a bijection
+//   h2  = rotl(hash64(word), rot)       hash64 (ssq_device.cuh) is a bijection
 //   home slot = top log2(cap) bits of h2 -> the table is ordered by hash, so a
 //               hash partition is a contiguous slot range (multi-GPU export,
 //               L2-sized insertion passes)
@@ -127,7 +127,7 @@ __device__ __forceinline__ u64 insert64_hashed(const TableView &t, u64 h2, u64 k
 }
 
 __device__ __forceinline__ u64 insert64(const TableView &t, u64 word, u32 len, u64 add, bool &is_new, bool defer_region = false) {
-    u64 h2 = rotl64(mix64(word), t.rot);
+    u64 h2 = table_hash64(word, t.rot);
     return insert64_hashed(t, h2, key64_of(h2, len), add, is_new, defer_region);
 }
 
@@ -143,7 +143,7 @@ __device__ __forceinline__ void add_region_counts(const TableView &t, bool is_ne
 
 __device__ __forceinline__ u64 find64(const TableView &t, u64 word, u32 len) {
     const u32 rmask = (1u << t.log2_region) - 1;
-    u64 h2 = rotl64(mix64(word), t.rot);
+    u64 h2 = table_hash64(word, t.rot);
     u64 key = key64_of(h2, len);
     const u64 home = h2 >> (64 - t.log2_cap);
     const u64 base = home & ~(u64)rmask;

@@ -1,7 +1,7 @@
 """Host-side (numpy) statement of the counter's key hash: which hash partition / rank owns a key.
 
 The device tables mix their own slot hash (the reference's dict hash, word0, is never
-observable): splitmix64 of the packed word for ShortSeq64 keys, a rotate-fold of the three
+observable): a fold-and-multiply bijection of the packed word for ShortSeq64 keys, a rotate-fold of the three
 words and the length followed by one splitmix64 round for ShortSeq192 keys (csrc/ssq_device.cuh).  The owner of a key in a
 P-way multi-GPU merge is the top log2(P) bits of that hash.  This module only computes
 partition ids for bookkeeping and tests; it counts nothing.
@@ -28,7 +28,8 @@ def key_hash(words, lens, klass):
     """64-bit key hash per read; words [n] (ShortSeq64) or [n, 3] (ShortSeq192)."""
     words = np.asarray(words, dtype=np.uint64)
     if klass == 0:
-        return mix64(words)
+        with np.errstate(over="ignore"):
+            return (words ^ (words >> np.uint64(32))) * _GOLD        # hash64 of csrc/ssq_device.cuh
     def rotl(x, r):
         return (x << np.uint64(r)) | (x >> np.uint64(64 - r))
     with np.errstate(over="ignore"):
