@@ -115,11 +115,48 @@ __global__ void wait_flags_kernel(const u64 *flags, int n, u64 epoch, DevReport 
     if (blockIdx.x == 0 && (int)threadIdx.x < n) wait_arrival(flags + threadIdx.x, epoch, rep);
 }
 
-__global__ void __launch_bounds__(kThreads, 3) merge_regions_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
-                                                                    const int64_t *region_bases, MergeRegions mr, const u64 *flags, u64 epoch) {
+// The probing scheme is count_regions2_kernel's (below): a lane makes ONE probe per tuple straight from registers; tuples
+// that did not settle are parked -- ballot-compacted -- in a warp-private queue and probed again 32 at a time, so no lane
+// waits for another lane's probe sequence (the first version ran every tuple's probe loop to its end, warp-wide: 7.7 warp
+// instructions per tuple, 2.4 ms per 1e8 tuples).  The region's counts are 64-bit DELTAS kept as two 32-bit halves: one
+// native 32-bit shared-memory atomic on the low half, the carry (and a sender count >= 2^32) added to the high half.
+constexpr int kMerge2Threads = 512;
+constexpr int kMerge2KPT = 2;
+constexpr int kMerge2Chunk = 32 * kMerge2KPT;
+constexpr int kMerge2Queue = 32 + kMerge2Chunk;          // a chunk is only started with fewer than 32 entries parked
+
+static size_t merge_regions2_smem(int log2_region) {
+    return ((size_t)16 << log2_region) + (size_t)20 * kMerge2Queue * (kMerge2Threads / 32);
+}
+
+// One probe of key (klo, khi) with weight `add` at slot `off`; true: found or inserted, delta added.
+__device__ __forceinline__ bool probe_once_weighted(u32 ks_a, u32 cs_a, u32 klo, u32 khi, u32 off, u64 add, u32 &my_new) {
+    u32 clo, chi;
+    lds_v2(ks_a + off * 8, clo, chi);
+    if (chi == 0) {                          // empty slot (a key's high word holds len + 1 in bits 58..63: never 0): claim it
+        const u64 old = atoms_cas_u64(ks_a + off * 8, 0ull, ((u64)khi << 32) | klo);
+        clo = (u32)old;
+        chi = (u32)(old >> 32);
+        if (chi == 0) { ++my_new; clo = klo; chi = khi; }
+    }
+    if (clo == klo && chi == khi) {
+        const u32 alo = (u32)add;
+        const u32 old = atoms_add_u32(cs_a + off * 8, alo);
+        const u32 hi_add = (u32)(add >> 32) + ((u32)(old + alo) < alo ? 1u : 0u);
+        if (hi_add) reds_add_u32(cs_a + off * 8 + 4, hi_add);
+        return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
+                                                                         const int64_t *region_bases, MergeRegions mr, const u64 *flags, u64 epoch) {
     extern __shared__ __align__(16) u64 dyn_region[];
-    __shared__ u32 s_new[kThreads / 32];
+    constexpr u32 W = kMerge2Threads / 32;
+    __shared__ u32 s_new[W];
     __shared__ int s_arrived;
+    __shared__ int64_t s_lo[kMaxMergeBlocks];
+    __shared__ u32 s_pre[kMaxMergeBlocks + 1];           // exclusive scan of this region's tuple counts per block
     if (flags != nullptr) {                                   // every sender's block must have landed before anything is read
         if (threadIdx.x == 0) s_arrived = 1;
         __syncthreads();
@@ -128,74 +165,130 @@ __global__ void __launch_bounds__(kThreads, 3) merge_regions_kernel(TableView t,
         if (!s_arrived) return;
     }
     const u32 R = 1u << t.log2_region, rmask = R - 1;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 *ks = dyn_region, *cs = dyn_region + R;
+    u64 *qk = dyn_region + 2 * R + warp * kMerge2Queue;                                           // parked keys of this warp
+    u64 *qc = dyn_region + 2 * R + (W + warp) * kMerge2Queue;                                     // their weights
+    u32 *qo = reinterpret_cast<u32 *>(dyn_region + 2 * R + 2 * W * kMerge2Queue) + warp * kMerge2Queue;   // slot | probes << 16
     const u32 region = blockIdx.x;
     ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
-    const bool was_empty = t.region_count[region] == 0;
-    for (u32 i = threadIdx.x; i < R; i += kThreads) {
-        const ulonglong2 v = was_empty ? make_ulonglong2(0ull, 0ull) : gslots[i];
-        ks[i] = v.x;
-        cs[i] = v.y;
+    if (warp == 0) {                                          // this region's tuple range in every block (loads overlap the region load)
+        int64_t lo = 0, hi = 0;
+        if ((int)lane < mr.n) {
+            const int64_t *rb = region_bases + (size_t)lane * mr.rb_stride;
+            lo = mr.off[lane] + rb[(size_t)region << mr.ratio_log2[lane]];
+            hi = mr.off[lane] + rb[((size_t)region + 1) << mr.ratio_log2[lane]];
+            s_lo[lane] = lo;
+        }
+        u32 incl = (u32)(hi - lo);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+        if ((int)lane < mr.n) s_pre[lane + 1] = incl;
+        if (lane == 0) s_pre[0] = 0;
     }
-    __shared__ int64_t s_lo[kMaxMergeBlocks], s_hi[kMaxMergeBlocks];
-    if ((int)threadIdx.x < mr.n) {                          // this region's tuple range in every block (loads overlap the region load)
-        const int b = threadIdx.x;
-        const int64_t *rb = region_bases + (size_t)b * mr.rb_stride;
-        s_lo[b] = mr.off[b] + rb[(size_t)region << mr.ratio_log2[b]];
-        s_hi[b] = mr.off[b] + rb[((size_t)region + 1) << mr.ratio_log2[b]];
+    const bool was_empty = t.region_count[region] == 0;
+    for (u32 i = threadIdx.x; i < R; i += kMerge2Threads) {
+        ks[i] = was_empty ? 0ull : gslots[i].x;
+        cs[i] = 0;
     }
     __syncthreads();
+    const u32 total = s_pre[mr.n];
     const int off_shift = 64 - t.log2_cap;
-    u32 my_new = 0, overflow = 0, bad = 0, touched = 0;
-    for (int b = 0; b < mr.n; b++) {
-        const int64_t lo = s_lo[b], hi = s_hi[b];
-        constexpr int kU = 4;                                      // tuples per thread in flight
-        for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)kU * kThreads) {
-            u64 wv[kU], av[kU];
-            u32 lv[kU];
+    const u32 ks_a = smem_addr(ks), cs_a = smem_addr(cs), qk_a = smem_addr(qk), qc_a = smem_addr(qc), qo_a = smem_addr(qo);
+    const u32 lt_mask = (1u << lane) - 1;
+    u32 my_new = 0, overflow = 0, bad = 0, seg = 0;
+    u32 qn = 0;                                          // warp-uniform: parked entries
+    auto park = [&](bool want, u32 klo, u32 khi, u64 add, u32 slot_probes) {
+        const u32 m = __ballot_sync(0xFFFFFFFFu, want);
+        if (want) {
+            const u32 at = qn + __popc(m & lt_mask);
+            sts_u64(qk_a + at * 8, ((u64)khi << 32) | klo);
+            sts_u64(qc_a + at * 8, add);
+            sts_u32(qo_a + at * 4, slot_probes);
+        }
+        qn += __popc(m);
+    };
+    auto serve = [&]() {                                 // pop up to 32 entries, one more probe each, re-park what is still unsettled
+        __syncwarp();
+        const u32 take = min(qn, 32u);
+        const u32 idx = qn - take + lane;
+        u32 klo = 0, khi = 0, sp = 0;
+        u64 add = 0;
+        const bool mine = lane < take;
+        if (mine) { lds_v2(qk_a + idx * 8, klo, khi); add = lds_u64(qc_a + idx * 8); sp = lds_u32(qo_a + idx * 4); }
+        __syncwarp();
+        qn -= take;
+        bool again = false;
+        if (mine) {
+            const u32 off = sp & 0xFFFFu, probes = sp >> 16;
+            if (probes > rmask) ++overflow;              // went around: the region is full
+            else if (!probe_once_weighted(ks_a, cs_a, klo, khi, off, add, my_new)) { again = true; sp = ((off + 1) & rmask) | ((probes + 1) << 16); }
+        }
+        park(again, klo, khi, add, sp);
+    };
+    u64 nw[kMerge2KPT], na[kMerge2KPT];
+    u32 nl[kMerge2KPT];
+    auto load_chunk = [&](u32 c) {
+        const u32 i0 = c * kMerge2Chunk;
+        while (i0 >= s_pre[seg + 1]) ++seg;                     // warp-uniform: the block the chunk starts in
+        u32 sg = seg;
 #pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const int64_t i = i0 + (int64_t)u * kThreads;
-                lv[u] = 0xFFFFFFFFu;
-                if (i < hi) { wv[u] = words[i]; av[u] = counts[i]; lv[u] = lens[i]; }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                if (lv[u] == 0xFFFFFFFFu) continue;
-                const u32 len = lv[u];
-                const u64 add = av[u];
-                const u64 h2 = table_hash64(wv[u], t.rot);
-                if (len > 32 || (u32)((h2 >> off_shift) >> t.log2_region) != region) { ++bad; continue; }   // not this region's tuple
-                const u64 key = key64_of(h2, len);
-                u32 off = (u32)(h2 >> off_shift) & rmask;
-                u32 left = R;
-                touched = 1;
-                for (;;) {
-                    u64 cur = *reinterpret_cast<volatile u64 *>(ks + off);
-                    if (cur == 0) {
-                        cur = atomicCAS(ks + off, 0ull, key);
-                        if (cur == 0) { ++my_new; cur = key; }
-                    }
-                    if (cur == key) { atomicAdd(cs + off, add); break; }
-                    off = (off + 1) & rmask;
-                    if (--left == 0) { ++overflow; break; }
-                }
-                __syncwarp(__activemask());
+        for (int r = 0; r < kMerge2KPT; r++) {
+            const u32 i = i0 + r * 32 + lane;
+            nl[r] = 0xFFFFFFFFu;
+            if (i < total) {
+                while (i >= s_pre[sg + 1]) ++sg;
+                const int64_t src = s_lo[sg] + (i - s_pre[sg]);
+                nw[r] = words[src];
+                na[r] = counts[src];
+                nl[r] = lens[src];
             }
         }
+    };
+    u32 c = warp;
+    if (c * kMerge2Chunk < total) load_chunk(c);
+    while (c * kMerge2Chunk < total) {
+        u64 wv[kMerge2KPT], av[kMerge2KPT];
+        u32 lv[kMerge2KPT];
+#pragma unroll
+        for (int j = 0; j < kMerge2KPT; j++) { wv[j] = nw[j]; av[j] = na[j]; lv[j] = nl[j]; }
+        c += W;
+        if (c * kMerge2Chunk < total) load_chunk(c);          // in flight during the probes
+#pragma unroll
+        for (int j = 0; j < kMerge2KPT; j++) {
+            bool pending = false;
+            u32 klo = 0, khi = 0, off = 0;
+            if (lv[j] != 0xFFFFFFFFu && av[j] != 0) {
+                const u64 h2 = table_hash64(wv[j], t.rot);
+                if (lv[j] > 32 || (u32)((h2 >> off_shift) >> t.log2_region) != region) ++bad;     // not this region's tuple
+                else {
+                    const u64 key = key64_of(h2, lv[j]);
+                    klo = (u32)key;
+                    khi = (u32)(key >> 32);
+                    off = (u32)(h2 >> off_shift) & rmask;
+                    pending = !probe_once_weighted(ks_a, cs_a, klo, khi, off, av[j], my_new);
+                }
+            }
+            park(pending, klo, khi, av[j], ((off + 1) & rmask) | (1u << 16));
+        }
+        while (qn >= 32) serve();
     }
-    const int any = __syncthreads_or((int)touched);
-    if (any)
-        for (u32 i = threadIdx.x; i < R; i += kThreads) gslots[i] = make_ulonglong2(ks[i], cs[i]);
+    while (qn > 0) serve();
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < R; i += kMerge2Threads) {
+        const u64 d = cs[i];
+        if (was_empty) gslots[i] = make_ulonglong2(ks[i], d);
+        else if (d) gslots[i] = make_ulonglong2(ks[i], gslots[i].y + d);
+    }
     if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
     if (bad) atomicMin(&t.rep->first_bad_len, 0ull);        // inconsistent blocks: surfaces as an error, never as wrong counts
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, d);
-    if ((threadIdx.x & 31) == 0) s_new[threadIdx.x >> 5] = my_new;
+    if (lane == 0) s_new[warp] = my_new;
     __syncthreads();
     if (threadIdx.x == 0) {
         u32 tot = 0;
-        for (int k = 0; k < kThreads / 32; k++) tot += s_new[k];
+        for (u32 k = 0; k < W; k++) tot += s_new[k];
         if (tot) { atomicAdd(t.size, (u64)tot); red_add_u32(t.region_count + region, tot); }
     }
 }
@@ -1991,10 +2084,10 @@ int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *
         if (rc0) return rc0;
         if (c->log2_cap != before || c->expected_unique <= 0) return plain();   // the region grid changed under the blocks / bound given up
     }
-    const size_t bytes = (size_t)16 << lr;
+    const size_t bytes = merge_regions2_smem(lr);
     int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
     if (rc) return rc;
-    merge_regions_kernel<<<(unsigned)my_regions, kThreads, bytes, ctx->stream>>>(view_of(c), words, lens, counts, region_bases, mr, flags, epoch);
+    merge_regions_kernel<<<(unsigned)my_regions, kMerge2Threads, bytes, ctx->stream>>>(view_of(c), words, lens, counts, region_bases, mr, flags, epoch);
     SSQ_LAUNCH_CHECK();
     return finish_pass(c);
 }

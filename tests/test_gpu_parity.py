@@ -633,6 +633,16 @@ def test_counter_merge_regions(sq, oracle, owner_unique):
     mine_expect = {k: v for (k, v), o in zip(expect.items(), own) if o == me}
     assert len(owner) == len(mine_expect)
     assert got == mine_expect
+    # a second merge into the now populated regions (loaded, only the touched slots written back), with weights whose
+    # low halves overflow 32 bits when added up: the carry into the high half of the 64-bit shared-memory deltas
+    big_w = (1 << 31) + 12345
+    counts2 = counts * big_w
+    owner.merge_regions_raw(words.data_ptr(), lens.data_ptr(), counts2.data_ptr(), total, [int(sz[me]) for sz in sizes],
+                            [per_owner] * P, rb.data_ptr(), per_owner + 1)
+    keys, cnt, _, _ = owner.export(1)
+    kw, kl, _ = keys.to_host()
+    assert len(owner) == len(mine_expect)
+    assert counter_dict(kw, kl, cnt.cpu().numpy()) == {k: v * (1 + big_w) for k, v in mine_expect.items()}
 
 
 @pytest.mark.parametrize("klass", [0, 1])
