@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--config", default="all", help="extra configs: all, none, or a comma list of " + ",".join(ALL_CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every extra config by this factor (development)")
+    ap.add_argument("--no-stream", action="store_true", help="N > 1: do not attach the counters (ssq_comm_attach): export + exchange after the pass")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange the uniques with NCCL all-to-all instead of peer stores")
     return ap.parse_args()
 
@@ -200,7 +201,7 @@ def config_of(args, world):
                     f"({u:.3g} distinct sequences in the generator), BASELINE.json configs[1]",
         "reads_per_gpu": n, "distinct_sequences": u, "read_len": L,
         "parallelism": (f"dp{world}: reads sharded by index, local tables merged by a hash-partitioned exchange of the uniques "
-                        f"({'torch.distributed all-to-all-v' if args.nccl_exchange else 'ssq_counter_merge_alltoall: export kernel stores into the owners over NVLink peer memory, device-side arrival flags'})")
+                        f"({'torch.distributed all-to-all-v' if args.nccl_exchange else 'ssq_comm_attach + ssq_counter_merge_alltoall: the region count kernel stores every counted region into its owner over NVLink peer memory, device-side arrival flags' if not args.no_stream else 'ssq_counter_merge_alltoall: export kernel stores into the owners over NVLink peer memory, device-side arrival flags'})")
         if world > 1 else "single GPU",
         "l2_policy": "inputs (>= 40 GB per step) far exceed the 126 MB L2; no flush needed",
     }
@@ -738,6 +739,8 @@ def run_ours(args, emit):
         owner = sq.DeviceCounter(klass, expected_unique=int(1.1 * u / world) + 1024, hash_rot=world.bit_length() - 1)
         if not args.nccl_exchange:
             comm = Comm(ctx)            # the library's own communicator: NCCL for the sizes, NVLink peer stores for the payload
+            if not args.no_stream:
+                comm.attach(local, owner)   # streamed exchange: the count kernel sends every table region to its owner as it goes
     state = {"comm": comm}
     h = ctx.bind()
     uniques_seen = [0]
@@ -843,6 +846,9 @@ def run_ours(args, emit):
                 "kernels": kernels}
 
     # the headline's buffers are no longer needed
+    streamed = bool(comm is not None and comm.last_streamed)
+    if comm is not None and comm.streams:
+        comm.attach(None, None)         # collective: frees the streamed exchange's receive buffers
     table_slots = local.capacity()
     del pt, local, owner
     free_gpu()
@@ -876,7 +882,9 @@ def run_ours(args, emit):
         if world > 1 and xms:
             line["exchange_ms"] = round(statistics.mean(x[0] for x in xms), 3)      # rank 0: send side (export kernel = peer stores)
             line["merge_ms"] = round(statistics.mean(x[1] for x in xms), 3)         # rank 0: wait for the senders + owner-side count
-            line["exchange"] = "peer stores over NVLink (ssq_counter_merge_alltoall)" if comm.peer_stores else "grouped ncclSend/ncclRecv (ssq_counter_merge_alltoall)"
+            line["exchange"] = ("streamed: count_regions2_kernel stores every counted region into its owner's memory over NVLink (ssq_comm_attach); "
+                                "the merge publishes arrival flags and adds the blocks up" if streamed else
+                                "peer stores over NVLink (ssq_counter_merge_alltoall)" if comm.peer_stores else "grouped ncclSend/ncclRecv (ssq_counter_merge_alltoall)")
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)

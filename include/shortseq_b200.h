@@ -253,12 +253,22 @@ int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t 
  *       owner's share into that owner's receive buffer over NVLink (CUDA IPC), arrival flags on the device, the owner
  *       counts region by region in shared memory.  ShortSeq192 / no IPC: grouped ncclSend / ncclRecv of a staged
  *       export.  exchange_ms / merge_ms (may be NULL): device time of this rank's send side and of its owner-side merge.
+ *   ssq_comm_attach      collective; the STREAMED exchange.  Binds a ShortSeq64 `local` counter (and the owner it will be
+ *       merged into) to the communicator: from then on the kernel that counts a table region during
+ *       ssq_counter_pack_count also stores that region's final (key, count) pairs into a fixed place of the owning rank's
+ *       receive buffer (over NVLink), so the transfer overlaps the count and ssq_counter_merge_alltoall has nothing left to
+ *       export: it publishes the arrival flags and merges.  Every rank must attach tables of the same capacity; *streams
+ *       (may be NULL) tells whether streaming is active (0: no CUDA IPC / regions do not nest -- merges take the path above).
+ *       A pass that cannot stream (table grown, direct-insert path) silently falls back for that merge, on every rank alike.
+ *       local == NULL detaches and frees the buffers (collective).
  *   A rank whose peers never deliver gets SSQ_ERR_EXCHANGE from the next ssq_ctx_sync (bounded device-side wait). */
 typedef struct ssq_comm ssq_comm;
 int ssq_comm_unique_id(uint8_t *id128);
 int ssq_comm_init(ssq_ctx *ctx, const uint8_t *id128, int rank, int world, ssq_comm **out);
 int ssq_comm_destroy(ssq_comm *comm);
 int ssq_comm_uses_peer_stores(ssq_comm *comm);
+int ssq_comm_attach(ssq_comm *comm, ssq_counter *local, ssq_counter *owner, int *streams);
+int ssq_comm_last_merge_streamed(ssq_comm *comm);   /* 1 when the last ssq_counter_merge_alltoall used the streamed regions */
 int ssq_counter_merge_alltoall(ssq_comm *comm, ssq_counter *local, ssq_counter *owner, float *exchange_ms, float *merge_ms);
 
 /* CUDA IPC for the peer exchange: handle64 = 64 opaque bytes to pass to the other single-GPU processes of the box. */

@@ -96,6 +96,8 @@ PROTOTYPES = {
     "ssq_comm_init": (_int, [_p, _p, _int, _int, C.POINTER(_p)]),
     "ssq_comm_destroy": (_int, [_p]),
     "ssq_comm_uses_peer_stores": (_int, [_p]),
+    "ssq_comm_attach": (_int, [_p, _p, _p, C.POINTER(C.c_int)]),
+    "ssq_comm_last_merge_streamed": (_int, [_p]),
     "ssq_counter_merge_alltoall": (_int, [_p, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 

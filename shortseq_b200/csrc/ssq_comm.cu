@@ -25,6 +25,7 @@
 #include <string.h>
 #include <vector>
 #include "ssq_internal.h"
+#include "ssq_table.cuh"
 
 namespace ssq {
 
@@ -33,6 +34,9 @@ int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *
                                const u64 *flags, u64 epoch);
 int counter_export_count_pass(ssq_counter *c, int n_parts, int64_t *part_counts);
 int counter_export_scatter_to(ssq_counter *c, int n_parts, u64 *const *dst_words, uint8_t *const *dst_lens, u64 *const *dst_counts);
+bool counter_stream_nests(const ssq_counter *owner, int n_blocks, int64_t block_regions, int log2_sregion);
+int counter_merge_streamed_impl(ssq_counter *c, const void *entries, const uint32_t *cnts, int n_blocks, int64_t block_regions,
+                                int log2_sregion, const u64 *flags, u64 epoch);
 
 struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId;
@@ -84,7 +88,8 @@ static NcclApi *nccl() {
     } while (0)
 
 constexpr int kMaxRanks = 32;
-enum { kBufWords = 0, kBufLens = 1, kBufCounts = 2, kBufBases = 3, kBufFlags = 4, kNumBufs = 5 };
+// kBufXE / kBufXC (+ parity): fixed-place receive buffers of the streamed exchange (ssq_comm_attach)
+enum { kBufWords = 0, kBufLens = 1, kBufCounts = 2, kBufBases = 3, kBufFlags = 4, kBufXE = 5, kBufXC = 7, kNumBufs = 9 };
 
 }  // namespace ssq
 
@@ -105,6 +110,14 @@ struct ssq_comm {
     void *stage[3];                       // staged path: local export buffers (words / lens / counts)
     int64_t stage_cap;
     cudaEvent_t ev[3];
+    // streamed exchange: a local counter attached with ssq_comm_attach sends its regions from inside the count kernel
+    ssq_stream_out so;
+    ssq_counter *attached;                // cleared by ssq_counter_destroy of that counter
+    bool x_ready;                         // the kBufXE / kBufXC buffers exist (collective state: the same on every rank)
+    int64_t x_block_regions;              // sender regions per (sender, owner) block
+    int x_log2_sregion;                   // log2(slots per sender region)
+    int64_t *d_xtable;                    // [5][world]: entry / count block pointers per parity, flag pointers
+    bool last_streamed;                   // the last merge took the streamed path
 };
 
 namespace ssq {
@@ -127,22 +140,40 @@ static int comm_barrier(ssq_comm *cm) {
     return SSQ_OK;
 }
 
-// Collective: unmap the peers' buffers, barrier, free this rank's (CUDA requires importers to close before the exporter frees).
-static int release_buffers(ssq_comm *cm, bool with_flags) {
-    const int last = with_flags ? kNumBufs : kBufFlags;
-    for (int k = 0; k < last; k++)
+// Collective: unmap the peers' buffers [first, last), barrier, free this rank's (CUDA requires importers to close before the
+// exporter frees).
+static int release_range(ssq_comm *cm, int first, int last) {
+    for (int k = first; k < last; k++)
         for (int r = 0; r < cm->world; r++) {
             if (r != cm->rank && cm->peer[k][r]) cudaIpcCloseMemHandle(cm->peer[k][r]);
             cm->peer[k][r] = nullptr;
         }
     int rc = comm_barrier(cm);
     if (rc) return rc;
-    for (int k = 0; k < last; k++) {
+    for (int k = first; k < last; k++) {
         if (cm->mine[k]) cudaFree(cm->mine[k]);
         cm->mine[k] = nullptr;
     }
-    if (!with_flags) { cm->cap = 0; cm->rb_cap = 0; }
     return SSQ_OK;
+}
+
+static int release_buffers(ssq_comm *cm, bool with_flags) {
+    int rc = release_range(cm, 0, with_flags ? kBufFlags + 1 : kBufFlags);
+    if (!with_flags) { cm->cap = 0; cm->rb_cap = 0; }
+    return rc;
+}
+
+static void detach_counter(ssq_comm *cm) {
+    if (cm->attached && cm->attached->stream_out == &cm->so) cm->attached->stream_out = nullptr;
+    cm->attached = nullptr;
+}
+
+static int release_stream_buffers(ssq_comm *cm) {
+    detach_counter(cm);
+    if (!cm->x_ready) return SSQ_OK;
+    cm->x_ready = false;
+    SSQ_CUDA(cudaStreamSynchronize(cm->ctx->stream));
+    return release_range(cm, kBufXE, kNumBufs);
 }
 
 // Collective: allocate buffers k in [first, last) with the given sizes, exchange their IPC handles, map the peers'.
@@ -267,8 +298,9 @@ int ssq_comm_init(ssq_ctx *ctx, const uint8_t *id128, int rank, int world, ssq_c
     SSQ_CUDA(cudaHostAlloc(&cm->h_table, 8 * 5 * (size_t)world, cudaHostAllocDefault));
     SSQ_CUDA(cudaMemsetAsync(cm->d_mine, 0, 8 * (world + 1), ctx->stream));
     for (int i = 0; i < 3; i++) SSQ_CUDA(cudaEventCreate(&cm->ev[i]));
+    SSQ_CUDA(cudaMalloc(&cm->d_xtable, 8 * 5 * (size_t)world));
     const size_t fbytes[1] = {(size_t)8 * world};
-    int rc = share_buffers(cm, kBufFlags, kNumBufs, fbytes);      // arrival flags: fixed size, shared once
+    int rc = share_buffers(cm, kBufFlags, kBufFlags + 1, fbytes);      // arrival flags: fixed size, shared once
     if (rc) return rc;
     *out = cm;
     return SSQ_OK;
@@ -278,7 +310,9 @@ int ssq_comm_destroy(ssq_comm *cm) {
     if (!cm) return SSQ_OK;
     DeviceGuard g(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
+    release_stream_buffers(cm);
     release_buffers(cm, true);
+    cudaFree(cm->d_xtable);
     for (int k = 0; k < 3; k++) if (cm->stage[k]) cudaFree(cm->stage[k]);
     cudaFree(cm->d_mine);
     cudaFree(cm->d_matrix);
@@ -293,6 +327,87 @@ int ssq_comm_destroy(ssq_comm *cm) {
 
 int ssq_comm_uses_peer_stores(ssq_comm *cm) { return cm && cm->peer_ok ? 1 : 0; }
 
+int ssq_comm_last_merge_streamed(ssq_comm *cm) { return cm && cm->last_streamed ? 1 : 0; }
+
+int ssq_comm_attach(ssq_comm *cm, ssq_counter *local, ssq_counter *owner, int *streams) {
+    SSQ_ARG(cm != nullptr, "communicator is NULL");
+    ssq_ctx *ctx = cm->ctx;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int P = cm->world, me = cm->rank;
+    if (streams) *streams = 0;
+    detach_counter(cm);
+    // what this rank proposes: the local table's capacity and the owner's hash rotation (-1: nothing to stream)
+    int64_t tag[2] = {-1, -1};
+    int lr = 0;
+    int64_t block_regions = 0;
+    if (local != nullptr && owner != nullptr && cm->peer_ok && local->klass == SSQ_CLASS_64 && owner->klass == SSQ_CLASS_64 &&
+        local->ctx == ctx && owner->ctx == ctx) {
+        lr = region_bits_for(local->log2_cap);
+        const int log2_regions = local->log2_cap - lr;
+        int log2_parts = 0;
+        while ((1 << log2_parts) < P) log2_parts++;
+        block_regions = ((int64_t)1 << log2_regions) >> log2_parts;
+        if (local->log2_cap >= 22 && lr <= 14 && log2_regions >= 6 && log2_regions >= log2_parts &&
+            counter_stream_nests(owner, P, block_regions, lr)) {
+            tag[0] = local->log2_cap;
+            tag[1] = owner->hash_rot;
+        }
+    }
+    SSQ_CUDA(cudaMemcpyAsync(cm->d_mine, tag, 16, cudaMemcpyHostToDevice, st));
+    SSQ_NCCL(nccl()->AllGather(cm->d_mine, cm->d_matrix, 2, ncclInt64, cm->comm, st));
+    SSQ_CUDA(cudaMemcpyAsync(cm->h_matrix, cm->d_matrix, 16 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    SSQ_CUDA(cudaStreamSynchronize(st));
+    bool same = tag[0] >= 0;
+    for (int r = 0; r < P; r++) same = same && cm->h_matrix[2 * r] == tag[0] && cm->h_matrix[2 * r + 1] == tag[1];
+    bool any = false;
+    for (int r = 0; r < P; r++) any = any || cm->h_matrix[2 * r] >= 0;
+    if (!same) {                                   // every rank sees the same matrix and takes the same road
+        int rc = release_stream_buffers(cm);
+        if (rc) return rc;
+        if (any && local != nullptr) { set_error("ssq_comm_attach: every rank must attach ShortSeq64 tables of the same capacity whose regions nest in the owner's"); return SSQ_ERR_ARG; }
+        return SSQ_OK;
+    }
+    if (!cm->x_ready || cm->so.log2_cap != local->log2_cap) {
+        int rc = release_stream_buffers(cm);
+        if (rc) return rc;
+        const size_t eb = (size_t)16 << local->log2_cap, cb = (size_t)4 * P * block_regions;
+        const size_t bytes[4] = {eb, eb, cb, cb};
+        rc = share_buffers(cm, kBufXE, kNumBufs, bytes);
+        if (rc) return rc;
+        cm->x_ready = true;
+        if (!cm->peer_ok) return release_stream_buffers(cm);      // a rank could not map: nobody streams
+    }
+    cm->x_block_regions = block_regions;
+    cm->x_log2_sregion = lr;
+    // this sender's block inside every owner's buffers, per parity; the owners' flag words
+    const size_t block_entries = (size_t)block_regions << lr;
+    for (int par = 0; par < 2; par++)
+        for (int d = 0; d < P; d++) {
+            cm->h_table[(0 + par) * P + d] = (int64_t)((ulonglong2 *)cm->peer[kBufXE + par][d] + (size_t)me * block_entries);
+            cm->h_table[(2 + par) * P + d] = (int64_t)((uint32_t *)cm->peer[kBufXC + par][d] + (size_t)me * block_regions);
+        }
+    for (int d = 0; d < P; d++) cm->h_table[4 * P + d] = (int64_t)cm->peer[kBufFlags][d];
+    SSQ_CUDA(cudaMemcpyAsync(cm->d_xtable, cm->h_table, 8 * 5 * (size_t)P, cudaMemcpyHostToDevice, st));
+    SSQ_CUDA(cudaStreamSynchronize(st));
+    cm->so.d_dst[0] = cm->d_xtable;
+    cm->so.d_dst[1] = cm->d_xtable + P;
+    cm->so.d_cnt[0] = cm->d_xtable + 2 * P;
+    cm->so.d_cnt[1] = cm->d_xtable + 3 * P;
+    cm->so.log2_parts = 0;
+    while ((1 << cm->so.log2_parts) < P) cm->so.log2_parts++;
+    cm->so.rot_owner = owner->hash_rot;
+    cm->so.rank = me;
+    cm->so.log2_cap = local->log2_cap;
+    cm->so.epoch = &cm->epoch;
+    cm->so.attached_slot = &cm->attached;
+    cm->attached = local;
+    local->stream_out = &cm->so;
+    local->streamed_seq = 0;
+    if (streams) *streams = 1;
+    return SSQ_OK;
+}
+
 int ssq_counter_merge_alltoall(ssq_comm *cm, ssq_counter *local, ssq_counter *owner, float *exchange_ms, float *merge_ms) {
     SSQ_ARG(cm != nullptr && local != nullptr && owner != nullptr, "NULL argument");
     SSQ_ARG(local->klass == owner->klass, "local and owner counters differ in class");
@@ -304,6 +419,38 @@ int ssq_counter_merge_alltoall(ssq_comm *cm, ssq_counter *local, ssq_counter *ow
     const int W = local->klass == SSQ_CLASS_64 ? 1 : 3;
     if (exchange_ms) *exchange_ms = 0.0f;
     if (merge_ms) *merge_ms = 0.0f;
+    cm->last_streamed = false;
+    if (cm->x_ready) {
+        // ---- streamed exchange: the regions already sit in the owners' buffers if every rank's last pass streamed them --------
+        const int par = (int)((cm->epoch + 1) & 1);
+        int64_t tag = -1;
+        if (cm->attached == local && local->stream_out == &cm->so && local->streamed_seq != 0 && local->streamed_seq == local->mod_seq &&
+            local->streamed_parity == par && local->log2_cap == cm->so.log2_cap && owner->hash_rot == cm->so.rot_owner &&
+            counter_stream_nests(owner, P, cm->x_block_regions, cm->x_log2_sregion))
+            tag = local->log2_cap;
+        SSQ_CUDA(cudaMemcpyAsync(cm->d_mine, &tag, 8, cudaMemcpyHostToDevice, st));
+        SSQ_NCCL(nccl()->AllGather(cm->d_mine, cm->d_matrix, 1, ncclInt64, cm->comm, st));
+        SSQ_CUDA(cudaMemcpyAsync(cm->h_matrix, cm->d_matrix, 8 * (size_t)P, cudaMemcpyDeviceToHost, st));
+        SSQ_CUDA(cudaStreamSynchronize(st));
+        bool all = tag >= 0;
+        for (int r = 0; r < P; r++) all = all && cm->h_matrix[r] == tag;
+        if (all) {
+            cm->last_streamed = true;
+            cm->epoch++;
+            SSQ_CUDA(cudaEventRecord(cm->ev[0], st));
+            signal_kernel<<<1, 32, 0, st>>>((u64 *const *)(cm->d_xtable + 4 * P), P, me, cm->epoch);
+            SSQ_LAUNCH_CHECK();
+            SSQ_CUDA(cudaEventRecord(cm->ev[1], st));
+            int rc2 = counter_merge_streamed_impl(owner, cm->mine[kBufXE + par], (const uint32_t *)cm->mine[kBufXC + par], P,
+                                                  cm->x_block_regions, cm->x_log2_sregion, (const u64 *)cm->mine[kBufFlags], cm->epoch);
+            if (rc2) return rc2;
+            SSQ_CUDA(cudaEventRecord(cm->ev[2], st));
+            SSQ_CUDA(cudaEventSynchronize(cm->ev[2]));
+            if (exchange_ms) SSQ_CUDA(cudaEventElapsedTime(exchange_ms, cm->ev[0], cm->ev[1]));
+            if (merge_ms) SSQ_CUDA(cudaEventElapsedTime(merge_ms, cm->ev[1], cm->ev[2]));
+            return SSQ_OK;
+        }
+    }
     int64_t local_regions = 0;
     ssq_counter_regions(local, &local_regions);
     const bool region_export = local->klass == SSQ_CLASS_64 && local_regions >= P;

@@ -149,8 +149,21 @@ __device__ __forceinline__ bool probe_once_weighted(u32 ks_a, u32 cs_a, u32 klo,
     return false;
 }
 
+// STREAMED: the blocks are the fixed-place receive buffers of the streamed exchange (count_regions2_kernel<., true>):
+// block b = sender b's entries[regions per owner][2^log2_sregion] of {key in THIS table's format, count} and
+// cnts[regions per owner]; an owner region is 2^ratio_log2 consecutive sender regions of every block.
+struct MergeStream {
+    const ulonglong2 *entries;
+    const u32 *cnts;
+    int64_t block_regions;        // sender regions per block
+    int log2_sregion;
+    int ratio_log2;
+};
+
+template <bool STREAMED>
 __global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
-                                                                         const int64_t *region_bases, MergeRegions mr, const u64 *flags, u64 epoch) {
+                                                                         const int64_t *region_bases, MergeRegions mr, MergeStream ms,
+                                                                         const u64 *flags, u64 epoch) {
     extern __shared__ __align__(16) u64 dyn_region[];
     constexpr u32 W = kMerge2Threads / 32;
     __shared__ u32 s_new[W];
@@ -172,18 +185,26 @@ __global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableV
     u32 *qo = reinterpret_cast<u32 *>(dyn_region + 2 * R + 2 * W * kMerge2Queue) + warp * kMerge2Queue;   // slot | probes << 16
     const u32 region = blockIdx.x;
     ulonglong2 *gslots = reinterpret_cast<ulonglong2 *>(t.slots) + ((size_t)region << t.log2_region);
+    const int nseg = STREAMED ? mr.n << ms.ratio_log2 : mr.n;       // <= 32: one lane each
     if (warp == 0) {                                          // this region's tuple range in every block (loads overlap the region load)
         int64_t lo = 0, hi = 0;
-        if ((int)lane < mr.n) {
-            const int64_t *rb = region_bases + (size_t)lane * mr.rb_stride;
-            lo = mr.off[lane] + rb[(size_t)region << mr.ratio_log2[lane]];
-            hi = mr.off[lane] + rb[((size_t)region + 1) << mr.ratio_log2[lane]];
+        if ((int)lane < nseg) {
+            if constexpr (STREAMED) {                         // segment = (sender block, sender region inside this region)
+                const int64_t sreg = ((int64_t)region << ms.ratio_log2) + (lane & ((1u << ms.ratio_log2) - 1));
+                const int64_t at = (int64_t)(lane >> ms.ratio_log2) * ms.block_regions + sreg;
+                lo = at << ms.log2_sregion;
+                hi = lo + min(ms.cnts[at], 1u << ms.log2_sregion);
+            } else {
+                const int64_t *rb = region_bases + (size_t)lane * mr.rb_stride;
+                lo = mr.off[lane] + rb[(size_t)region << mr.ratio_log2[lane]];
+                hi = mr.off[lane] + rb[((size_t)region + 1) << mr.ratio_log2[lane]];
+            }
             s_lo[lane] = lo;
         }
         u32 incl = (u32)(hi - lo);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
-        if ((int)lane < mr.n) s_pre[lane + 1] = incl;
+        if ((int)lane < nseg) s_pre[lane + 1] = incl;
         if (lane == 0) s_pre[0] = 0;
     }
     const bool was_empty = t.region_count[region] == 0;
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableV
         cs[i] = 0;
     }
     __syncthreads();
-    const u32 total = s_pre[mr.n];
+    const u32 total = s_pre[nseg];
     const int off_shift = 64 - t.log2_cap;
     const u32 ks_a = smem_addr(ks), cs_a = smem_addr(cs), qk_a = smem_addr(qk), qc_a = smem_addr(qc), qo_a = smem_addr(qo);
     const u32 lt_mask = (1u << lane) - 1;
@@ -239,9 +260,16 @@ __global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableV
             if (i < total) {
                 while (i >= s_pre[sg + 1]) ++sg;
                 const int64_t src = s_lo[sg] + (i - s_pre[sg]);
-                nw[r] = words[src];
-                na[r] = counts[src];
-                nl[r] = lens[src];
+                if constexpr (STREAMED) {
+                    const ulonglong2 e = ms.entries[src];
+                    nw[r] = e.x;
+                    na[r] = e.y;
+                    nl[r] = 0;
+                } else {
+                    nw[r] = words[src];
+                    na[r] = counts[src];
+                    nl[r] = lens[src];
+                }
             }
         }
     };
@@ -258,7 +286,18 @@ __global__ void __launch_bounds__(kMerge2Threads, 2) merge_regions_kernel(TableV
         for (int j = 0; j < kMerge2KPT; j++) {
             bool pending = false;
             u32 klo = 0, khi = 0, off = 0;
-            if (lv[j] != 0xFFFFFFFFu && av[j] != 0) {
+            if (STREAMED && lv[j] != 0xFFFFFFFFu && av[j] != 0) {
+                // the entry is a table key already: its slot bits below the top six must name this region
+                const u32 slot_low = (u32)((wv[j] & kMask58) >> off_shift);
+                const u32 len1 = (u32)(wv[j] >> 58);
+                if (len1 == 0 || len1 > 33 || (slot_low >> t.log2_region) != (region & ((1u << (t.log2_cap - t.log2_region - 6)) - 1))) ++bad;
+                else {
+                    klo = (u32)wv[j];
+                    khi = (u32)(wv[j] >> 32);
+                    off = slot_low & rmask;
+                    pending = !probe_once_weighted(ks_a, cs_a, klo, khi, off, av[j], my_new);
+                }
+            } else if (!STREAMED && lv[j] != 0xFFFFFFFFu && av[j] != 0) {
                 const u64 h2 = table_hash64(wv[j], t.rot);
                 if (lv[j] > 32 || (u32)((h2 >> off_shift) >> t.log2_region) != region) ++bad;     // not this region's tuple
                 else {
@@ -705,11 +744,27 @@ __device__ __forceinline__ bool probe_once(u32 ks_a, u32 ds_a, u32 klo, u32 khi,
     return false;
 }
 
-template <int THREADS>
+// Streamed exchange (multi-GPU, ssq_comm_attach): the CTA that has just counted a region also compacts the region's final
+// (key, count) pairs -- still in shared memory -- and stores them into the receive buffer of the rank that owns the
+// region's hash range, over NVLink when that is another GPU.  Every (sender, sender region) has a FIXED place there
+// (2^log2_region entries + one count), so nothing has to be sized or scanned first: the export pass over the table, the
+// size matrix and the region-offset arrays of the unstreamed exchange disappear, and the transfer overlaps the count.
+// Keys travel in the OWNER table's format (its hash rotation applied), so the owner's merge does not hash at all.
+struct StreamOut {
+    ulonglong2 *const *dst;      // [1 << log2_parts] this sender's entry block in every owner's receive buffer
+    u32 *const *dst_cnt;         // [1 << log2_parts] this sender's count block there
+    int log2_parts;
+    int rot_owner;
+    u32 first_region;            // CTA b counts region (b + first_region) mod regions: rank r starts with owner r + 1, so
+                                 // that at any moment every owner receives from one sender
+};
+
+template <int THREADS, bool STREAM>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3)
-count_regions2_kernel(TableView t, RegionParts rp) {
+count_regions2_kernel(TableView t, RegionParts rp, StreamOut so) {
     extern __shared__ __align__(16) u64 dyn_region[];
     __shared__ u32 s_new[THREADS / 32];
+    __shared__ u32 s_out;
     constexpr u32 W = THREADS / 32;
     const u32 R = 1u << t.log2_region, rmask = R - 1;
     u64 *ks = dyn_region;
@@ -719,7 +774,7 @@ count_regions2_kernel(TableView t, RegionParts rp) {
     u32 *qo = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + W * kCount2Queue) + warp * kCount2Queue;   // slot | probes << 16
     u32 *pre = reinterpret_cast<u32 *>(dyn_region + R + R / 2 + W * kCount2Queue) + W * kCount2Queue;    // [nseg + 1] exclusive scan of the segment sizes
     u32 *segoff = pre + (rp.slices << (8 - rp.qbits)) + 1;                        // [nseg] first entry of stream segment k in rp.keys
-    const u32 region = blockIdx.x;
+    const u32 region = STREAM ? (blockIdx.x + so.first_region) & (gridDim.x - 1) : blockIdx.x;
     const u32 sub_bits = 8 - rp.qbits, sub_mask = (1u << sub_bits) - 1;
     const u32 p = region >> rp.qbits, q = region & ((1u << rp.qbits) - 1);
     const u32 nseg = rp.slices << sub_bits;
@@ -747,6 +802,7 @@ count_regions2_kernel(TableView t, RegionParts rp) {
         ks[i] = was_empty ? 0ull : ld_hint_v2u64(gslots + i, keep).x;
         ds[i] = 0;
     }
+    if (STREAM && threadIdx.x == 0) s_out = 0;
     __syncthreads();
     const u32 total = pre[nseg];
     const u32 hi_shift = (u32)(64 - t.log2_cap) - 32;   // the home slot's region offset lies in the key's high word
@@ -832,10 +888,40 @@ count_regions2_kernel(TableView t, RegionParts rp) {
     }
     while (qn > 0) serve();
     __syncthreads();
-    for (u32 i = threadIdx.x; i < R; i += THREADS) {
-        const u32 d = ds[i];
-        if (was_empty) gslots[i] = make_ulonglong2(ks[i], (u64)d);
-        else if (d) gslots[i] = make_ulonglong2(ks[i], gslots[i].y + d);
+    if constexpr (!STREAM) {
+        for (u32 i = threadIdx.x; i < R; i += THREADS) {
+            const u32 d = ds[i];
+            if (was_empty) gslots[i] = make_ulonglong2(ks[i], (u64)d);
+            else if (d) gslots[i] = make_ulonglong2(ks[i], gslots[i].y + d);
+        }
+    } else {
+        // write-back + the region's final tuples to their owner (R and THREADS are multiples of 32: a warp is in or out as one)
+        const int log2_regions = t.log2_cap - t.log2_region;
+        const u32 owner = region >> (log2_regions - so.log2_parts);
+        const u32 in_owner = region & ((1u << (log2_regions - so.log2_parts)) - 1);
+        ulonglong2 *out = so.dst[owner] + ((size_t)in_owner << t.log2_region);
+        const u64 top6 = (u64)(region >> (log2_regions - 6)) << 58;
+        for (u32 i = threadIdx.x; i < R; i += THREADS) {
+            const u32 d = ds[i];
+            const u64 k = ks[i];
+            u64 cnt = d;
+            if (was_empty) gslots[i] = make_ulonglong2(k, cnt);
+            else if (k != 0) {                                   // keys of earlier passes travel too, with their whole count
+                cnt += gslots[i].y;
+                if (d) gslots[i] = make_ulonglong2(k, cnt);
+            }
+            const bool occ = k != 0;
+            const u32 m = __ballot_sync(0xFFFFFFFFu, occ);
+            u32 base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_out, (u32)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (occ) {
+                const u64 h = rotr64(top6 | (k & kMask58), t.rot);          // hash64(word)
+                out[base + __popc(m & lt_mask)] = make_ulonglong2((rotl64(h, so.rot_owner) & kMask58) | (k & ~kMask58), cnt);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) so.dst_cnt[owner][in_owner] = s_out;
     }
     if (overflow) atomicAdd(&t.rep->table_overflow, (u64)overflow);
 #pragma unroll
@@ -1297,6 +1383,7 @@ static int log2_cap_for(int64_t expected_unique) {
 // Grow to 2^new_log2 slots, rehashing on the device.  The stream is idle on entry and on exit.
 static int grow(ssq_counter *c, int new_log2) {
     ssq_ctx *ctx = c->ctx;
+    c->mod_seq++;
     cudaStream_t st = ctx->stream;
     const size_t nslots = (size_t)1 << new_log2;
     void *nslots_p = nullptr;
@@ -1503,6 +1590,32 @@ static int set_max_smem(const void *kernel, size_t bytes) {
     return SSQ_OK;
 }
 
+template <int THREADS>
+static int launch_count_regions2(ssq_counter *c, const TableView &t, const RegionParts &rp, unsigned nregions, size_t bytes, bool stream) {
+    cudaStream_t st = c->ctx->stream;
+    StreamOut so{};
+    int rc;
+    if (stream) {
+        const ssq_stream_out *x = c->stream_out;
+        const int par = (int)((*x->epoch + 1) & 1);
+        so.dst = (ulonglong2 *const *)x->d_dst[par];
+        so.dst_cnt = (u32 *const *)x->d_cnt[par];
+        so.log2_parts = x->log2_parts;
+        so.rot_owner = x->rot_owner;
+        so.first_region = (u32)((unsigned)((x->rank + 1) & ((1 << x->log2_parts) - 1)) * (nregions >> x->log2_parts));
+        rc = set_max_smem((const void *)count_regions2_kernel<THREADS, true>, bytes);
+        if (rc) return rc;
+        count_regions2_kernel<THREADS, true><<<nregions, THREADS, bytes, st>>>(t, rp, so);
+        c->streamed_seq = c->mod_seq;
+        c->streamed_parity = par;
+    } else {
+        rc = set_max_smem((const void *)count_regions2_kernel<THREADS, false>, bytes);
+        if (rc) return rc;
+        count_regions2_kernel<THREADS, false><<<nregions, THREADS, bytes, st>>>(t, rp, so);
+    }
+    return SSQ_OK;
+}
+
 // Phase 2 of the deferred path: count the keys of the level-1 partitions `pv` into the table.
 // ev_mid (may be null) is recorded between the level-2 scatter and the region count.
 static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cudaEvent_t ev_mid) {
@@ -1533,22 +1646,22 @@ static int launch_count_parts(ssq_counter *c, int64_t n, const PartView &pv, cud
     const unsigned nregions = 1u << (t.log2_cap - t.log2_region);
     const unsigned nseg = rp.slices << (8 - rp.qbits);
     const int cthreads = env_int("SSQ_COUNT_THREADS", t.log2_region >= 14 ? 512 : 384, 256, 512);   // one CTA per SM at 2^14-slot regions: make it a big one
+    // attached to a communicator whose receive buffers match this table: the count kernel also sends every region to its owner
+    const bool stream = c->stream_out != nullptr && c->stream_out->log2_cap == c->log2_cap &&
+                        t.log2_cap - t.log2_region >= 6 && t.log2_cap - t.log2_region >= c->stream_out->log2_parts;
     if (env_int("SSQ_COUNT_V2", 1, 0, 1)) {
         if (cthreads == 256) {
             const size_t bytes = count_regions2_smem<256>(t.log2_region, nseg);
-            rc = set_max_smem((const void *)count_regions2_kernel<256>, bytes);
+            rc = launch_count_regions2<256>(c, t, rp, nregions, bytes, stream);
             if (rc) return rc;
-            count_regions2_kernel<256><<<nregions, 256, bytes, ctx->stream>>>(t, rp);
         } else if (cthreads == 512) {
             const size_t bytes = count_regions2_smem<512>(t.log2_region, nseg);
-            rc = set_max_smem((const void *)count_regions2_kernel<512>, bytes);
+            rc = launch_count_regions2<512>(c, t, rp, nregions, bytes, stream);
             if (rc) return rc;
-            count_regions2_kernel<512><<<nregions, 512, bytes, ctx->stream>>>(t, rp);
         } else {
             const size_t bytes = count_regions2_smem<384>(t.log2_region, nseg);
-            rc = set_max_smem((const void *)count_regions2_kernel<384>, bytes);
+            rc = launch_count_regions2<384>(c, t, rp, nregions, bytes, stream);
             if (rc) return rc;
-            count_regions2_kernel<384><<<nregions, 384, bytes, ctx->stream>>>(t, rp);
         }
     } else if (cthreads == 256) {
         const size_t bytes = count_regions_smem<256>(t.log2_region, nseg);
@@ -1603,6 +1716,7 @@ int pack_count_impl(ssq_counter *c, const uint8_t *ascii, int64_t lo, int64_t hi
     ssq_ctx *ctx = c->ctx;
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
     int rc = SSQ_OK;
+    c->mod_seq++;
     if (c->expected_unique > 0 && (rc = make_room(c, n)) != SSQ_OK) return rc;
     if (c->expected_unique <= 0) {
         c->last_pass_phases = 0;
@@ -1704,6 +1818,7 @@ int ssq_counter_destroy(ssq_counter *c) {
     if (!c) return SSQ_OK;
     DeviceGuard g(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
+    if (c->stream_out && c->stream_out->attached_slot) *c->stream_out->attached_slot = nullptr;   // the communicator forgets this counter
     cudaFree(c->slots);
     cudaFree(c->first_idx);
     cudaFree(c->region_count);
@@ -1723,6 +1838,7 @@ int ssq_counter_clear(ssq_counter *c) {
     SSQ_ARG(c != nullptr, "counter is NULL");
     DeviceGuard g(c->ctx->device);
     const size_t nslots = (size_t)1 << c->log2_cap;
+    c->mod_seq++;
     SSQ_CUDA(cudaMemsetAsync(c->slots, 0, nslots * slot_bytes(c->klass), c->ctx->stream));
     SSQ_CUDA(cudaMemsetAsync(c->d_size, 0, sizeof(u64), c->ctx->stream));
     c->known_size = 0;
@@ -1738,6 +1854,7 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
     if (n == 0) return SSQ_OK;
     ssq_ctx *ctx = c->ctx;
     DeviceGuard g(ctx->device);
+    c->mod_seq++;
     const int W = c->klass == SSQ_CLASS_64 ? 1 : 3;
     if (c->expected_unique > 0) {
         int rc0 = make_room(c, n);
@@ -2085,9 +2202,52 @@ int counter_merge_regions_impl(ssq_counter *c, const u64 *words, const uint8_t *
         if (c->log2_cap != before || c->expected_unique <= 0) return plain();   // the region grid changed under the blocks / bound given up
     }
     const size_t bytes = merge_regions2_smem(lr);
-    int rc = set_max_smem((const void *)merge_regions_kernel, bytes);
+    int rc = set_max_smem((const void *)merge_regions_kernel<false>, bytes);
     if (rc) return rc;
-    merge_regions_kernel<<<(unsigned)my_regions, kMerge2Threads, bytes, ctx->stream>>>(view_of(c), words, lens, counts, region_bases, mr, flags, epoch);
+    merge_regions_kernel<false><<<(unsigned)my_regions, kMerge2Threads, bytes, ctx->stream>>>(view_of(c), words, lens, counts, region_bases, mr,
+                                                                                             MergeStream{}, flags, epoch);
+    SSQ_LAUNCH_CHECK();
+    return finish_pass(c);
+}
+
+// Owner side of the streamed exchange: entries / cnts are this rank's receive buffers (n_blocks sender blocks of
+// block_regions sender regions of 2^log2_sregion entries).  SSQ_ERR_ARG when the region grids do not nest -- the caller
+// checked that before anything was streamed (counter_stream_nests).
+bool counter_stream_nests(const ssq_counter *owner, int n_blocks, int64_t block_regions, int log2_sregion) {
+    const int lr = region_bits_for(owner->log2_cap);
+    const int64_t my_regions = (int64_t)1 << (owner->log2_cap - lr);
+    int r = 0;
+    while ((my_regions << r) < block_regions) r++;
+    return owner->klass == SSQ_CLASS_64 && owner->expected_unique > 0 && lr <= 12 && owner->log2_cap - lr >= 6 &&
+           (my_regions << r) == block_regions && ((int64_t)n_blocks << r) <= kMaxMergeBlocks && log2_sregion >= 1 && log2_sregion <= 16;
+}
+
+int counter_merge_streamed_impl(ssq_counter *c, const void *entries, const uint32_t *cnts, int n_blocks, int64_t block_regions,
+                                int log2_sregion, const u64 *flags, u64 epoch) {
+    SSQ_ARG(c != nullptr && entries != nullptr && cnts != nullptr && n_blocks >= 1, "bad arguments");
+    ssq_ctx *ctx = c->ctx;
+    DeviceGuard g(ctx->device);
+    if (!counter_stream_nests(c, n_blocks, block_regions, log2_sregion)) { set_error("streamed merge: the region grids do not nest"); return SSQ_ERR_ARG; }
+    const int before = c->log2_cap;
+    int rc = make_room(c, INT64_MAX / 4);                    // the number of incoming tuples is not known: the caller's bound decides
+    if (rc) return rc;
+    if (c->log2_cap != before || c->expected_unique <= 0) { set_error("streamed merge: the owner table had to grow"); return SSQ_ERR_ARG; }
+    c->mod_seq++;
+    const int lr = region_bits_for(c->log2_cap);
+    const int64_t my_regions = (int64_t)1 << (c->log2_cap - lr);
+    MergeRegions mr{};
+    mr.n = n_blocks;
+    MergeStream ms;
+    ms.entries = (const ulonglong2 *)entries;
+    ms.cnts = cnts;
+    ms.block_regions = block_regions;
+    ms.log2_sregion = log2_sregion;
+    ms.ratio_log2 = 0;
+    while ((my_regions << ms.ratio_log2) < block_regions) ms.ratio_log2++;
+    const size_t bytes = merge_regions2_smem(lr);
+    rc = set_max_smem((const void *)merge_regions_kernel<true>, bytes);
+    if (rc) return rc;
+    merge_regions_kernel<true><<<(unsigned)my_regions, kMerge2Threads, bytes, ctx->stream>>>(view_of(c), nullptr, nullptr, nullptr, nullptr, mr, ms, flags, epoch);
     SSQ_LAUNCH_CHECK();
     return finish_pass(c);
 }

@@ -34,6 +34,17 @@ struct ssq_ctx {
     size_t scratch_bytes;
 };
 
+// Streamed exchange (ssq_comm_attach): owned by an ssq_comm; a counter attached to it sends every region of its
+// deferred passes to the owners' receive buffers from inside the count kernel (ssq_counter.cu: StreamOut).
+struct ssq_stream_out {
+    void *d_dst[2];               // device arrays [P] of entry-block pointers (this sender's block in every owner), per parity
+    void *d_cnt[2];               // device arrays [P] of count-block pointers, per parity
+    int log2_parts, rot_owner, rank;
+    int log2_cap;                 // the local table geometry the receive buffers are sized for
+    const uint64_t *epoch;        // the communicator's merge counter: a pass streams into parity (*epoch + 1) & 1
+    struct ssq_counter **attached_slot;   // the communicator's pointer to the attached counter (cleared when that counter dies)
+};
+
 struct ssq_counter {
     ssq_ctx *ctx;
     int klass;            // SSQ_CLASS_64 | SSQ_CLASS_192
@@ -59,6 +70,10 @@ struct ssq_counter {
     int64_t region_segs;       // segments the count array is sized for
     cudaEvent_t ev[4];         // last bounded pass: start / after pack+scatter / after the region scatter / end
     int last_pass_phases;      // 0 none, 1 direct single kernel, 2 deferred (scatter + count)
+    ssq_stream_out *stream_out;   // non-null while attached to a communicator (ssq_comm_attach)
+    uint64_t mod_seq;             // bumped by everything that changes keys or counts
+    uint64_t streamed_seq;        // mod_seq of the pass whose regions were streamed (valid while == mod_seq)
+    int streamed_parity;          // receive-buffer parity that pass wrote
 };
 
 namespace ssq {

@@ -107,12 +107,27 @@ class Comm:
         _lib.check(lib.ssq_comm_init(ctx.bind(), uid, self.rank, self.world, C.byref(h)))
         self.handle = h
         self.exchange_ms, self.merge_ms = 0.0, 0.0
+        self.streams, self._attached, self.last_streamed = False, None, False
 
     @property
     def peer_stores(self):
         """True when ShortSeq64 merges go over NVLink peer stores (CUDA IPC available on every rank)."""
         from . import _lib
         return bool(_lib.lib().ssq_comm_uses_peer_stores(self.handle))
+
+    def attach(self, local, owner):
+        """Collective: ssq_comm_attach -- from now on `local`'s counting passes stream every table region to its owner rank
+        from inside the count kernel, and merge(local, owner) only publishes the arrival flags and merges.  Returns True
+        when streaming is active (ShortSeq64 tables of one capacity on every rank, CUDA IPC available)."""
+        import ctypes as C
+        from . import _lib
+        self.ctx.bind()
+        on = C.c_int(0)
+        _lib.check(_lib.lib().ssq_comm_attach(self.handle, local.handle if local is not None else None,
+                                              owner.handle if owner is not None else None, C.byref(on)))
+        self.streams = bool(on.value)
+        self._attached = (local, owner)          # keep the counters alive while the library points at them
+        return self.streams
 
     def merge(self, local, owner):
         """Collective: add every rank's `local` counter into the per-rank `owner` tables (owner must have been created
@@ -124,6 +139,7 @@ class Comm:
         e, m = C.c_float(), C.c_float()
         _lib.check(_lib.lib().ssq_counter_merge_alltoall(self.handle, local.handle, owner.handle, C.byref(e), C.byref(m)))
         self.exchange_ms, self.merge_ms = e.value, m.value
+        self.last_streamed = bool(_lib.lib().ssq_comm_last_merge_streamed(self.handle))
         _batch.raise_for_report(self.ctx.sync())
         return owner
 
