@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 3) scatter_packed_kernel(TableView t
 // A CTA's input of the level-2 scatter / the region count: a few segments read as one concatenated stream.
 // pre[k] = number of keys in the segments before segment k (pre[nseg] = total); each thread walks the
 // segments monotonically, so the segment of an index is found by advancing a private cursor.
-constexpr int kMaxStreamSegs = 512;
+constexpr int kMaxStreamSegs = 640;       // scatter CTAs of the fused pack pass (148 SMs x up to 4)
 
 // Level 2: CTA (p, s) reads slice s of the level-1 segments of partition p (scatter CTAs [c0, c1)) and appends
 // every key to the segment of its level-2 partition (hash bits 55..48).  The loads of the next tile are in

@@ -498,7 +498,10 @@ __global__ void __launch_bounds__(kPackThreads, (KLASS == SSQ_CLASS_192 && MODE 
 // kernel's semantics.  The CTA only synchronises to flush the staging rings.  The host picks this kernel when the
 // batch holds exactly 32 n bytes (launch_fixed); everything else is decided here, tile by tile.
 constexpr int kWarpTileReads = 64;
-constexpr int kPack32FlushEvery = 4;        // warp tiles between two flushes: 8 warps x 4 x 64 = 2048 keys, as pack_fixed_kernel
+#ifndef SSQ_PACK32_FLUSH
+#define SSQ_PACK32_FLUSH 4
+#endif
+constexpr int kPack32FlushEvery = SSQ_PACK32_FLUSH;   // warp tiles between two flushes: 8 warps x 4 x 64 = 2048 keys, as pack_fixed_kernel
 
 // One read the slow way (any length, any alignment): returns false when the read must not be counted.
 __device__ __noinline__ bool pack32_slow_read(const PackArgs &a, int64_t i, u64 &word, u32 &len_out) {
@@ -521,8 +524,11 @@ __device__ __noinline__ bool pack32_slow_read(const PackArgs &a, int64_t i, u64 
     return !bad;
 }
 
+#ifndef SSQ_PACK32_MIN_BLOCKS
+#define SSQ_PACK32_MIN_BLOCKS 3      /* development: 4 (<= 64 registers) needs 32 KB staging rings (SSQ_LINE_KEYS=8) */
+#endif
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 3) pack32_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : SSQ_PACK32_MIN_BLOCKS) pack32_kernel(PackArgs a, TableView t, PartView pv, const u64 *stop) {
     extern __shared__ __align__(16) u64 dyn_ring[];
     __shared__ u32 s_head[MODE == kModeScatter ? kParts : 1];
     __shared__ u32 s_tail[MODE == kModeScatter ? kParts : 1];
