@@ -84,6 +84,49 @@ __global__ void __launch_bounds__(kThreads) insert_kernel(TableView t, const u64
     block_add_new(t, my_new, s_new);
 }
 
+// ShortSeq192 direct inserts with the home slots of a thread's keys loaded TOGETHER (one 256-bit load each, L2 evict_last)
+// before the first probe, as count_parts192_kernel does.  The weighted insert of a multi-GPU merge receives its tuples in
+// the senders' table order -- nearly this table's order -- so the slots stream through L2 while the probes run.
+constexpr int kIns192 = 2;
+__global__ void __launch_bounds__(kThreads) insert192_pre_kernel(TableView t, const u64 *words, const uint8_t *lens, const u64 *counts,
+                                                                 int64_t n, int64_t index_base, const u64 *stop) {
+    __shared__ u32 s_new[kThreads / 32];
+    if (stop != nullptr && *stop != 0) return;
+    const u64 keep = l2_policy_evict_last();
+    const int sh = 64 - t.log2_cap;
+    u32 my_new = 0;
+    for (int64_t i0 = (int64_t)blockIdx.x * (kThreads * kIns192); i0 < n; i0 += (int64_t)gridDim.x * (kThreads * kIns192)) {
+        u64 w0[kIns192], w1[kIns192], w2[kIns192], add[kIns192], h2[kIns192];
+        u32 len[kIns192];
+        bool ok[kIns192];
+#pragma unroll
+        for (int j = 0; j < kIns192; j++) {
+            const int64_t i = i0 + j * kThreads + threadIdx.x;
+            ok[j] = i < n;
+            if (ok[j]) {
+                w0[j] = words[3 * i]; w1[j] = words[3 * i + 1]; w2[j] = words[3 * i + 2];
+                len[j] = lens[i];
+                add[j] = counts ? counts[i] : 1ull;
+                if (!len_in_class(SSQ_CLASS_192, len[j])) { atomicMin(&t.rep->first_bad_len, (u64)(index_base + i)); ok[j] = false; }
+                else if (add[j] == 0) ok[j] = false;
+                else h2[j] = rotl64(hash192(w0[j], w1[j], w2[j], len[j]), t.rot);
+            }
+        }
+        u64 sm[kIns192], s0[kIns192], s1[kIns192], s2[kIns192];
+#pragma unroll
+        for (int j = 0; j < kIns192; j++)
+            if (ok[j]) ld_relaxed_v4u64_hint(t.slots + 4 * (h2[j] >> sh), keep, sm[j], s0[j], s1[j], s2[j]);
+#pragma unroll
+        for (int j = 0; j < kIns192; j++) {
+            if (!ok[j]) continue;
+            bool is_new = false;
+            insert192_impl<true>(t, h2[j], w0[j], w1[j], w2[j], len[j], add[j], is_new, sm[j], s0[j], s1[j], s2[j]);
+            my_new += is_new ? 1u : 0u;
+        }
+    }
+    block_add_new(t, my_new, s_new);
+}
+
 constexpr int kMaxMergeBlocks = 32;
 
 // Region-aligned weighted merge (ShortSeq64 owner tables of a multi-GPU merge).  Every sender's block is ordered by
@@ -1878,8 +1921,8 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
                 insert_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens,
                                                                                 (const u64 *)counts, n, 0, nullptr);
             else
-                insert_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(view_of(c), (const u64 *)words, lens,
-                                                                                 (const u64 *)counts, n, 0, nullptr);
+                insert192_pre_kernel<<<grid_for(ctx, (n + kThreads * kIns192 - 1) / (kThreads * kIns192), 8), kThreads, 0, ctx->stream>>>(
+                    view_of(c), (const u64 *)words, lens, (const u64 *)counts, n, 0, nullptr);
             SSQ_LAUNCH_CHECK();
         }
         if (rc) return rc;
@@ -1893,7 +1936,7 @@ static int insert_common(ssq_counter *c, const uint64_t *words, const uint8_t *l
         if (c->klass == SSQ_CLASS_64)
             insert_kernel<SSQ_CLASS_64><<<grid, kThreads, 0, ctx->stream>>>(t, w, lens + p, cn, cnt, p, stop);
         else
-            insert_kernel<SSQ_CLASS_192><<<grid, kThreads, 0, ctx->stream>>>(t, w, lens + p, cn, cnt, p, stop);
+            insert192_pre_kernel<<<grid_for(ctx, (cnt + kThreads * kIns192 - 1) / (kThreads * kIns192), 8), kThreads, 0, ctx->stream>>>(t, w, lens + p, cn, cnt, p, stop);
         SSQ_LAUNCH_CHECK();
         return SSQ_OK;
     });
