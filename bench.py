@@ -825,8 +825,10 @@ def run_ours(args, emit):
         if regions:
             kernels.append(kern("ssq::region_scatter_kernel", "route keys to their 4096-slot table region (second 256-way scatter); "
                                 "shares the count phase's algorithmic bytes with the region count", p_ms[1], 0))
-            kernels.append(kern("ssq::count_regions2_kernel<384>", "count each region's keys in shared memory, write the table back",
-                                p_ms[2], count_bytes))
+            kernels.append(kern("ssq::count_regions2_kernel<384,%s>" % ("true" if (comm is not None and comm.streams) else "false"),
+                                "count each region's keys in shared memory, write the table back"
+                                + (" and store the region's (key, count) pairs into the owner rank's receive buffer (streamed exchange)"
+                                   if (comm is not None and comm.streams) else ""), p_ms[2], count_bytes))
             kernels[-1]["achieved_gbs"] = round(count_bytes / ((p_ms[1] + p_ms[2]) * 1e-3) / 1e9, 1)   # over both count-phase kernels
             kernels[-1]["frac"] = round(kernels[-1]["achieved_gbs"] / peak, 4)
         else:

@@ -6,8 +6,8 @@ o=gpurun_out
 mkdir -p $o
 python -c "import __graft_entry__ as g; g.smoke()" > $o/${tag}_smoke.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 >> $o/${tag}_smoke.txt
-timeout 900 python bench.py > $o/${tag}_bench_n1.json 2> $o/${tag}_bench_n1.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference_arm.json 2>> $o/${tag}_bench_n1.err
+t0=$(date +%s); timeout 900 python bench.py > $o/${tag}_bench_n1.json 2> $o/${tag}_bench_n1.err; echo "bench.py wall: $(( $(date +%s) - t0 )) s" >> $o/${tag}_smoke.txt
+t0=$(date +%s); timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference_arm.json 2>> $o/${tag}_bench_n1.err; echo "bench.py --impl reference wall: $(( $(date +%s) - t0 )) s" >> $o/${tag}_smoke.txt
 # launch list of the bench command (kernel shares of the step); never a bench value
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --config none --no-cpu-baseline --no-e2e --no-parity > $o/${tag}_ncu_launches.log 2>&1
