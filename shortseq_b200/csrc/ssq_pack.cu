@@ -632,10 +632,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : SSQ_PACK32_MIN_B
                     key[q] = key64_of(h2[q], 32u);
                     part[q] = (u32)(h2[q] >> 56);
                 }
+#ifdef SSQ_X_NOSTAGE      /* development: the keys leave coalesced, no staging at all (what the scatter itself costs) */
+                pv.keys[first + r0] = key[0] + part[0];
+                pv.keys[first + r0 + 16] = key[1] + part[1];
+                staged[0] = staged[1] = true;
+#else
                 stage_keys<2>(stg, part, key, ok2, staged);
 #pragma unroll
                 for (int q = 0; q < 2; q++)
                     if (!staged[q]) insert64_slow(t, h2[q], key[q], &s_unstaged_new);
+#endif
             }
         } else if (wt < ntiles) {
             // a tile that is not 64 aligned 32-nt reads (or the ragged end of the batch): lane-per-read
