@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(kThreads) hammingvar_kernel(const u64 *a, cons
 
 // Query x reference set.  The refs (words + lengths) are staged in shared memory in chunks;
 // every thread owns one query and scans the chunk.
-constexpr int kRefChunk = 1024;
+constexpr int kRefChunk = 1024;       // the (distance << 10 | index) packing below relies on it
+static_assert(kRefChunk <= 1024, "chunk index must fit in 10 bits");
 template <int W>
 __global__ void __launch_bounds__(kThreads) refset_kernel(const u64 *q, const uint8_t *lq, int64_t nq, const u64 *refs,
                                                           const uint8_t *lr, int nr, int thresh, uint8_t *min_dist,
@@ -531,14 +532,31 @@ __global__ void __launch_bounds__(kThreads) refset_kernel(const u64 *q, const ui
             const int uniform = __syncthreads_and(same);      // the usual case: every reference of the chunk has one length
             if (mine && uniform) {
                 if (qlen == len0) {
+                    // (distance, index in chunk) travel as one number, so that min + argmin are one IMNMX per reference
+                    // (the smaller index wins a tie, as `d < best` in index order does)
+                    u32 bestk = 0xFFFFFFFFu;
+                    if (W == 1 && len0 <= 16) {
+                        // UMIs: <= 16 bases live in the low 32 bits (bits >= 2 len are zero): half the XOR / collapse work
+                        const u32 q32 = (u32)qw[0];
+                        const u32 *r32 = reinterpret_cast<const u32 *>(s_ref);
+#pragma unroll 8
+                        for (int j = 0; j < cnt; j++) {
+                            const u32 x = q32 ^ r32[2 * j];
+                            const u32 d = __popc(((x >> 1) | x) & 0x55555555u);
+                            bestk = min(bestk, (d << 10) | (u32)j);
+                            within += (int)d <= thresh ? 1 : 0;
+                        }
+                    } else {
 #pragma unroll 4
-                    for (int j = 0; j < cnt; j++) {
-                        int d = 0;
+                        for (int j = 0; j < cnt; j++) {
+                            u32 d = 0;
 #pragma unroll
-                        for (int k = 0; k < W; k++) d += diff_bases(qw[k], s_ref[j * W + k]);
-                        if (d < best) { best = d; best_j = (u32)(r0 + j); }
-                        within += d <= thresh ? 1 : 0;
+                            for (int k = 0; k < W; k++) d += (u32)diff_bases(qw[k], s_ref[j * W + k]);
+                            bestk = min(bestk, (d << 10) | (u32)j);
+                            within += (int)d <= thresh ? 1 : 0;
+                        }
                     }
+                    if (cnt > 0 && (int)(bestk >> 10) < best) { best = (int)(bestk >> 10); best_j = (u32)r0 + (bestk & 1023u); }
                 }
             } else if (mine) {
                 for (int j = 0; j < cnt; j++) {

@@ -214,7 +214,9 @@ def test_hamming_length_mismatch(sq):
 
 def test_hamming_refset(sq):
     rng = np.random.default_rng(60)
-    for klass, L in ((0, 12), (1, 96)):
+    # 12 / 16 nt: the 32-bit UMI loop; 20 / 32 nt: one 64-bit word; 96 nt: three words.  1500 references = one uniform
+    # chunk + one chunk with a second length in it; ties in the distance are common (first minimal index wins)
+    for klass, L in ((0, 12), (0, 16), (0, 20), (0, 32), (1, 96)):
         refs = rand_reads(rng, 1500, L, L) + rand_reads(rng, 10, L - 1, L - 1)
         q = rand_reads(rng, 3000, L, L)
         Q, R = sq.pack_batch(q, klass=klass), sq.pack_batch(refs, klass=klass)
