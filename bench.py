@@ -971,7 +971,9 @@ def run_e2e(sq, args, world, rank, state, barrier, h):
            "reads_per_step": ne, "ms_per_step": round(e_ms, 3),
            "host_link_gbs_per_gpu": round((h2d + d2h[0]) / (e_ms * 1e-3) / 1e9, 1),
            "call": "ssq_host_pack_count_lens (pinned host ASCII + one uint8 length per read in, packed words out, 4M-read "
-                   "chunks, H2D / kernel / D2H overlapped on three streams), then export of (keys, lengths, counts) to pinned host memory"}
+                   "chunks, H2D / kernel / D2H overlapped on three streams), then export of (keys, lengths, counts) to pinned host memory",
+           "sample": f"{ne} reads per GPU per step: a slice of the {int(args.reads):.3g}-read workload from the same generator with the "
+                     "reads-per-distinct-key ratio kept (33 B of pinned host memory per read; the rate is PCIe-bound and does not depend on the slice)"}
     del ectr, eowner, h_ascii, h_words
     free_gpu()
     return res
