@@ -659,6 +659,24 @@ def cfg_c5(sq, args, peak):
         out[name] = res
         del a, b, d
     free_gpu()
+    # the consumer of the UMI Hamming kernel (row N3): UMI-tools' directional clustering of the distinct 12-nt UMIs of many
+    # groups (one group per mapping position): all pairs inside a group, label propagation until stable, one CTA per group
+    try:
+        groups, per = max(1024, int(2e5 * args.scale)), 32
+        nu = groups * per
+        umis = sq.pack_batch(sq.synth_reads(nu, nu, 12, 12, seed=SEED + 123), klass=sq.CLASS_64)
+        cnt = torch.randint(1, 50, (nu,), dtype=torch.int64, device=umis.words.device)
+        goff = torch.arange(0, nu + 1, per, dtype=torch.int64, device=umis.words.device)
+        ms = timed(lambda: sq.umi_collapse(umis, cnt, goff, 1, "directional"), 3, 1)
+        rep, ccounts, ncl = sq.umi_collapse(umis, cnt, goff, 1, "directional")
+        out["umi_collapse"] = {"groups": groups, "umis_per_group": per, "threshold": 1, "method": "directional", "ms": round(ms, 3),
+                               "gpairs_per_sweep_s": round(groups * per * per / (ms * 1e-3) / 1e9, 1),
+                               "mumis_s": round(nu / ms / 1e3, 1), "clusters": int(ncl.sum().item()),
+                               "counts_conserved": bool(int(ccounts.sum().item()) == int(cnt.sum().item()))}
+        del umis, cnt, goff, rep, ccounts, ncl
+    except Exception as e:  # noqa: BLE001 -- reported, not fatal
+        out["umi_collapse"] = {"error": repr(e)[:300]}
+    free_gpu()
     return out
 
 
