@@ -248,6 +248,59 @@ constexpr int kUmiThreads = 256;
 constexpr int kUmiSmemGroup = 4096;
 struct UmiScratch { u32 *label, *by_rank; };
 
+// Groups of at most 32 UMIs -- the usual case, one group per mapping position -- are clustered by ONE WARP each: a lane
+// holds one UMI in registers, ranks and labels travel by shuffles, no shared memory and no block barrier (a 256-thread CTA
+// per 30-UMI group left seven of its eight warps idle at every barrier).
+__global__ void __launch_bounds__(kUmiThreads) umi_cluster_small_kernel(const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *group_off,
+                                                                        int64_t n_groups, int threshold, int method, int64_t *rep, int64_t *n_clusters) {
+    const u32 lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kUmiThreads + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * kUmiThreads) >> 5;
+    for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        const int64_t base = group_off[g];
+        const int64_t n64 = group_off[g + 1] - base;
+        if (n64 > 32) continue;                                   // umi_cluster_kernel's
+        const u32 n = (u32)n64;
+        if (n == 0) { if (lane == 0 && n_clusters) n_clusters[g] = 0; continue; }
+        const bool mine = lane < n;
+        const u64 wv = mine ? words[base + lane] : 0ull;
+        const u64 cv = mine ? counts[base + lane] : 0ull;
+        const u32 lv = mine ? lens[base + lane] : 0xFFu;
+        // rank: decreasing count, ties in input order
+        u32 label = 0;
+        for (u32 u = 0; u < n; u++) {
+            const u64 cu = __shfl_sync(0xFFFFFFFFu, cv, u);
+            label += (cu > cv || (cu == cv && u < lane)) ? 1u : 0u;
+        }
+        const u32 rank = label;
+        // the minimum label flows along the edges until a sweep changes nothing
+        for (;;) {
+            u32 best = label;
+            for (u32 u = 0; u < n; u++) {
+                const u64 wu = __shfl_sync(0xFFFFFFFFu, wv, u);
+                const u64 cu = __shfl_sync(0xFFFFFFFFu, cv, u);
+                const u32 lu = __shfl_sync(0xFFFFFFFFu, lv, u);
+                const u32 bu = __shfl_sync(0xFFFFFFFFu, label, u);
+                if (!mine || bu >= best || lu != lv) continue;
+                if (method == 0 && cu + 1 < 2 * cv) continue;            // directional: count[u] >= 2 count[v] - 1
+                if (diff_bases(wu, wv) <= threshold) best = bu;
+            }
+            const bool changed = best < label;
+            label = best;
+            if (!__any_sync(0xFFFFFFFFu, changed)) break;
+        }
+        // representative = the UMI whose rank is this UMI's final label
+        u32 rep_lane = 0;
+        for (u32 u = 0; u < n; u++) {
+            const u32 ru = __shfl_sync(0xFFFFFFFFu, rank, u);
+            if (ru == label) rep_lane = u;
+        }
+        if (mine) rep[base + lane] = base + rep_lane;
+        const u32 heads = __ballot_sync(0xFFFFFFFFu, mine && rep_lane == lane);
+        if (lane == 0 && n_clusters) n_clusters[g] = __popc(heads);
+    }
+}
+
+template <bool SKIP_SMALL>
 __global__ void __launch_bounds__(kUmiThreads) umi_cluster_kernel(const u64 *words, const uint8_t *lens, const u64 *counts, const int64_t *group_off,
                                                                   int64_t n_groups, int threshold, int method, int64_t *rep, int64_t *n_clusters,
                                                                   UmiScratch sc) {
@@ -256,6 +309,7 @@ __global__ void __launch_bounds__(kUmiThreads) umi_cluster_kernel(const u64 *wor
     for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int64_t base = group_off[g];
         const u32 n = (u32)(group_off[g + 1] - base);
+        if (SKIP_SMALL && group_off[g + 1] - base <= 32) continue;     // umi_cluster_small_kernel's (CTA-uniform: no barrier is skipped by a part of the CTA)
         if (n == 0) { if (threadIdx.x == 0 && n_clusters) n_clusters[g] = 0; continue; }
         const bool staged = n <= (u32)kUmiSmemGroup;
         // word (8) | count (8) | len (1, padded) | label (4) | by_rank (4)
@@ -336,12 +390,17 @@ int ssq_umi_cluster(ssq_ctx *ctx, const uint64_t *words, const uint8_t *lens, co
     const size_t smem = (size_t)ssq::kUmiSmemGroup * (8 + 8 + 4 + 4 + 1) + 16;
     static bool configured = false;
     if (!configured) {
-        SSQ_CUDA(cudaFuncSetAttribute(ssq::umi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSQ_CUDA(cudaFuncSetAttribute(ssq::umi_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    // small groups: a warp each; everything else: a CTA each (that kernel skips the small ones)
+    const int sgrid = ssq::grid_for(ctx, (n_groups + ssq::kUmiThreads / 32 - 1) / (ssq::kUmiThreads / 32), 8);
+    ssq::umi_cluster_small_kernel<<<sgrid, ssq::kUmiThreads, 0, ctx->stream>>>((const ssq::u64 *)words, lens, (const ssq::u64 *)counts, group_off, n_groups,
+                                                                             threshold, method, rep, n_clusters);
+    SSQ_LAUNCH_CHECK();
     const int grid = ssq::grid_for(ctx, n_groups, 2);
-    ssq::umi_cluster_kernel<<<grid, ssq::kUmiThreads, smem, ctx->stream>>>((const ssq::u64 *)words, lens, (const ssq::u64 *)counts, group_off, n_groups,
-                                                                         threshold, method, rep, n_clusters, sc);
+    ssq::umi_cluster_kernel<true><<<grid, ssq::kUmiThreads, smem, ctx->stream>>>((const ssq::u64 *)words, lens, (const ssq::u64 *)counts, group_off, n_groups,
+                                                                               threshold, method, rep, n_clusters, sc);
     SSQ_LAUNCH_CHECK();
     return SSQ_OK;
 }

@@ -56,7 +56,7 @@ def umi_tools_groups(umis, counts, threshold, method):
 @pytest.mark.parametrize("threshold", [1, 2])
 def test_umi_collapse_matches_umi_tools_rules(sq, method, threshold):
     rng = np.random.default_rng(7 + threshold)
-    group_sizes = [1, 2, 37, 300, 0, 900]
+    group_sizes = [1, 2, 37, 300, 0, 900, 32, 33, 31, 5, 17, 24, 32, 8]      # <= 32: a warp per group; larger: a CTA per group
     umis, counts, goff = [], [], [0]
     for gs in group_sizes:
         seeds = ["".join(rng.choice(list("ACGT"), size=10)) for _ in range(max(1, gs // 6))]
