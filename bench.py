@@ -758,7 +758,10 @@ def run_ours(args, emit):
         if not args.nccl_exchange:
             comm = Comm(ctx)            # the library's own communicator: NCCL for the sizes, NVLink peer stores for the payload
             if not args.no_stream:
-                comm.attach(local, owner)   # streamed exchange: the count kernel sends every table region to its owner as it goes
+                try:
+                    comm.attach(local, owner)   # streamed exchange: the count kernel sends every table region to its owner as it goes
+                except Exception as e:  # noqa: BLE001 -- the decision is collective (every rank sees the same matrix): all ranks land here together
+                    print(f"[bench] streamed exchange unavailable, merging unstreamed: {e!r}", file=sys.stderr)
     state = {"comm": comm}
     h = ctx.bind()
     uniques_seen = [0]
