@@ -555,11 +555,12 @@ __global__ void __launch_bounds__(THREADS, 3) region_scatter_kernel(TableView t,
     // Tiles never straddle segments, so a tile's keys sit at consecutive addresses.  (seg, pos) = where the next tile
     // to LOAD starts; both are CTA-uniform.
     u32 seg = 0, pos = 0;
+    u32 seg_len = nseg ? pre[1] : 0u;           // keys of segment `seg`: re-read only when the segment changes
     u64 nk[kScatterRounds];
     auto load_tile = [&]() -> u32 {             // returns the number of keys of the tile (0 = stream exhausted)
-        while (seg < nseg && pos >= pre[seg + 1] - pre[seg]) { ++seg; pos = 0; }
+        while (seg < nseg && pos >= seg_len) { ++seg; pos = 0; seg_len = seg < nseg ? pre[seg + 1] - pre[seg] : 0u; }
         if (seg >= nseg) return 0u;
-        const u32 here = min(pre[seg + 1] - pre[seg] - pos, kTile);
+        const u32 here = min(seg_len - pos, kTile);
         const u64 *src = part0 + seg * seg_stride + pos + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < kScatterRounds; j++) nk[j] = (u32)(j * THREADS) + threadIdx.x < here ? ld_stream_u64(src + j * THREADS, drop) : 0ull;
