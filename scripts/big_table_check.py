@@ -1,6 +1,9 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Consistency of the deferred counting paths on tables beyond 2^28 slots (development aid): 2^29 slots = 8192-slot
 regions counted in shared memory, 2^30 slots = the L2-ordered fallback; both against a direct-insert counter."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
 import torch
 import shortseq_b200 as sq

@@ -1,6 +1,9 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Device timings of the BASELINE.json configs that are not the bench line (development aid): ShortSeqVar pack + decode
 round trip, batched Hamming (pairs and against a reference set), ShortSeq64/192 decode.  Algorithmic bytes per SURVEY 8d."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import shortseq_b200 as sq
 

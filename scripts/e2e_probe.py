@@ -1,4 +1,7 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C, time, sys, torch
 import shortseq_b200 as sq
 from shortseq_b200 import _lib

@@ -1,6 +1,9 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """End-to-end timing of the GPU FASTQ ingest (host text buffer -> counts) next to the reference's read_and_count_fastq
 on a smaller file (development aid).  usage: fastq_bench.py [n_reads] [n_distinct] [read_len]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import time
 

@@ -1,5 +1,8 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Times the pieces of the multi-GPU merge on one GPU: export grouped by owner, weighted merge of one owner's share."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, time, torch
 import shortseq_b200 as sq
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10**9

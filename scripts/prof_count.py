@@ -1,6 +1,8 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Runs the fused pack+count a few times (for ncu captures)."""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import shortseq_b200 as sq
 from shortseq_b200 import _lib

@@ -1,6 +1,8 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Runs each kernel a few times at a mid size (for ncu captures: -k regex:<name> -s 1 -c 1)."""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import shortseq_b200 as sq
 from shortseq_b200 import _lib
