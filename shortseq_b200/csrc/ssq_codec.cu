@@ -655,9 +655,7 @@ int ssq_decode_tiles(ssq_ctx *ctx, const uint8_t *lens, int64_t n, int max_len, 
     DeviceGuard g(ctx->device);
     const int64_t ntiles = (n + kDecTile - 1) / kDecTile;
     if (ntiles == 0) { SSQ_CUDA(cudaMemsetAsync(tile_base, 0, sizeof(int64_t), ctx->stream)); return SSQ_OK; }
-    void *scratch = nullptr;     // tile totals live after the scan's own scratch need: take a separate allocation-free slot
     int64_t *totals = tile_base + ntiles + 1;          // the caller's buffer holds 2 * ntiles + 2 entries: [bases | totals]
-    (void)scratch;
     tile_totals_kernel<<<grid_for(ctx, (ntiles + kThreads / 32 - 1) / (kThreads / 32), 8), kThreads, 0, ctx->stream>>>(lens, n, max_len, totals);
     SSQ_LAUNCH_CHECK();
     return scan_i64(ctx, totals, ntiles, tile_base);
