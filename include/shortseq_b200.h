@@ -259,7 +259,9 @@ int ssq_counter_export_to(ssq_counter *c, int n_parts, int first_part, uint64_t 
  *       receive buffer (over NVLink), so the transfer overlaps the count and ssq_counter_merge_alltoall has nothing left to
  *       export: it publishes the arrival flags and merges.  Every rank must attach tables of the same capacity; *streams
  *       (may be NULL) tells whether streaming is active (0: no CUDA IPC / regions do not nest -- merges take the path above).
- *       A pass that cannot stream (table grown, direct-insert path) silently falls back for that merge, on every rank alike.
+ *       A pass that cannot stream (table grown, direct-insert path) silently falls back for that merge, on every rank alike;
+ *       attach again after `local` has grown.  Every streamed pass sends the WHOLE table (earlier passes' keys included):
+ *       attach before the one large pass, or the last one, not around a chunked ingest.
  *       local == NULL detaches and frees the buffers (collective).
  *   A rank whose peers never deliver gets SSQ_ERR_EXCHANGE from the next ssq_ctx_sync (bounded device-side wait). */
 typedef struct ssq_comm ssq_comm;
