@@ -45,3 +45,30 @@ def owner_rank(words, lens, klass, world):
         return np.zeros(len(np.asarray(lens)), dtype=np.int64)
     bits = world.bit_length() - 1
     return (key_hash(words, lens, klass) >> np.uint64(64 - bits)).astype(np.int64)
+
+
+# ---- the ShortSeq64 table key and its journey through the streamed multi-GPU exchange (csrc/ssq_table.cuh, ssq_counter.cu) ----
+_MASK58 = np.uint64((1 << 58) - 1)
+
+
+def _rotl(x, r):
+    x = np.asarray(x, dtype=np.uint64)
+    r %= 64
+    return x if r == 0 else (x << np.uint64(r)) | (x >> np.uint64(64 - r))
+
+
+def table_key64(words, lens, rot):
+    """(h2, key) of ShortSeq64 keys in a table with hash rotation `rot`: h2 = rotl(hash64(word), rot); the stored key is
+    h2's low 58 bits with len + 1 in bits 58..63 (key64_of); the home slot of a 2^c-slot table is h2 >> (64 - c)."""
+    h2 = _rotl(key_hash(words, lens, 0), rot)
+    key = (h2 & _MASK58) | ((np.asarray(lens, dtype=np.uint64) + np.uint64(1)) << np.uint64(58))
+    return h2, key
+
+
+def streamed_key64(local_key, region, log2_regions, rot_local, rot_owner):
+    """What count_regions2_kernel<., true> sends for a slot of table region `region` holding `local_key`: the key in the
+    OWNER table's format.  The six hash bits a key does not store are the top six bits of its region index."""
+    local_key = np.asarray(local_key, dtype=np.uint64)
+    top6 = (np.asarray(region, dtype=np.uint64) >> np.uint64(log2_regions - 6)) << np.uint64(58)
+    h = _rotl(top6 | (local_key & _MASK58), 64 - rot_local)          # hash64(word)
+    return (_rotl(h, rot_owner) & _MASK58) | (local_key & ~_MASK58)

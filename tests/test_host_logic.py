@@ -127,3 +127,35 @@ def test_fastq_line_rule_matches_reference(tmp_path):
             mine[r.decode()] = mine.get(r.decode(), 0) + 1
         theirs = collections.OrderedDict((str(k), v) for k, v in ref.read_and_count_fastq(str(p)).items())
         assert mine == theirs and list(mine) == list(theirs)
+
+
+def test_streamed_exchange_key_conversion():
+    """The host statement of the streamed exchange's key rewrite (ssq_counter.cu, count_regions2_kernel<., true>): a key
+    read from a slot of the sender's table, together with its region index, becomes the owner table's key; the owner's
+    region and slot offset are bits of that key, and the owner rank is the top log2(P) bits of the unrotated hash."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    lens = rng.integers(1, 33, size=n).astype(np.uint8)
+    words = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) >> (np.uint64(64) - 2 * lens.astype(np.uint64))
+    for world, log2_cap_local, log2_cap_owner in ((2, 28, 27), (8, 28, 25), (4, 22, 20), (1, 22, 22), (2, 28, 26)):
+        rot_o = world.bit_length() - 1
+        lr = 12
+        log2_regions = log2_cap_local - lr
+        h2, key = hashing.table_key64(words, lens, 0)
+        region = (h2 >> np.uint64(64 - log2_cap_local)) >> np.uint64(lr)            # home region = the region a key is found in
+        sent = hashing.streamed_key64(key, region, log2_regions, 0, rot_o)
+        h2_o, key_o = hashing.table_key64(words, lens, rot_o)
+        assert np.array_equal(sent, key_o)
+        # the owner of the region the key sat in is the key's owner rank
+        owner = region >> np.uint64(log2_regions - rot_o) if rot_o else np.zeros(n, np.uint64)
+        assert np.array_equal(owner.astype(np.int64), hashing.owner_rank(words, lens, 0, world))
+        # merge_regions_kernel<true>: region and offset in the owner table from the key alone (minus the six top bits)
+        off_shift = 64 - log2_cap_owner
+        slot_low = (sent & np.uint64((1 << 58) - 1)) >> np.uint64(off_shift)
+        slot = h2_o >> np.uint64(off_shift)
+        assert np.array_equal(slot_low & np.uint64((1 << lr) - 1), slot & np.uint64((1 << lr) - 1))
+        assert np.array_equal(slot_low >> np.uint64(lr), (slot >> np.uint64(lr)) & np.uint64((1 << (log2_cap_owner - lr - 6)) - 1))
+        # the sender's region in_owner index refines the owner's region index (the grids nest)
+        in_owner = region & np.uint64((1 << (log2_regions - rot_o)) - 1)
+        ratio = (log2_regions - rot_o) - (log2_cap_owner - lr)
+        assert ratio >= 0 and np.array_equal(in_owner >> np.uint64(ratio), slot >> np.uint64(lr))
